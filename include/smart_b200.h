@@ -1,0 +1,150 @@
+/*
+ * smart_b200.h -- C ABI of the B200-native SMART hot path (libsmart_b200.so).
+ *
+ * What it replaces.  The reference (ThibHlln/smartpy v0.2.2) has exactly one native plug
+ * point for this path: an optional module `smartcpp` (smartpy/structure.py:22-27) whose
+ * `allsteps` replaces run_all_steps (call sites structure.py:118-121 and :143-146) and
+ * whose `onestep` replaces run_one_step (structure.py:171-174, :182-187).  That contract is
+ * one member at a time.  The entry points below keep it (smart_allsteps_host) and add the
+ * batch form the Monte-Carlo layer needs (smartpy/montecarlo/montecarlo.py:179-209 is a
+ * per-sample Python loop in the reference): N members (parameter set x catchment) stepped
+ * in one launch, with the objective functions of montecarlo.py:193-209 fused in.
+ *
+ * Conventions
+ *   - plain C types only; every pointer in smart_batch_desc is a DEVICE pointer borrowed
+ *     for the duration of the (stream-ordered) call, except in the *_host entry points
+ *     where every pointer is a HOST pointer;
+ *   - no hidden allocation and no implicit synchronisation in the device entry points;
+ *   - return value 0 = success, negative = SMART_ERR_*; smart_last_error() gives the text;
+ *   - parameter order is the reference's Parameters.names (smartpy/parameters.py:25):
+ *     T, C, H, D, S, Z, SK, FK, GK, RK;
+ *   - the 19-vector order is the reference's model_variables (structure.py:78-82):
+ *     Q_aeva, Q_ove, Q_dra, Q_int, Q_sgw, Q_dgw, Q_out, V_ove, V_dra, V_int, V_sgw, V_dgw,
+ *     V_ly1..V_ly6, V_river  (fluxes m3/s, volumes m3).
+ */
+#ifndef SMART_B200_H
+#define SMART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMART_B200_VERSION 100 /* 0.1.0 */
+
+#define SMART_N_PARAMS 10
+#define SMART_N_VARS 19
+#define SMART_N_SCORES 8    /* NSE, KGE, KGEc, KGEa, KGEb, PBias, RMSE, GW (montecarlo.py:71-74) */
+#define SMART_OBS_STATS 6   /* n_valid, sum_e, mean_e, sum(e-mean_e), sum((e-mean_e)^2), reserved */
+
+#define SMART_REPORT_SUMMARY 1 /* structure.py:65-66, :190 */
+#define SMART_REPORT_RAW 2     /* structure.py:67-68, :193 */
+
+#define SMART_OK 0
+#define SMART_ERR_BAD_ARG (-1)       /* null/misaligned pointer, non-positive size, unknown report type */
+#define SMART_ERR_WARMUP_TOO_LONG (-2) /* structure.py:90-95 */
+#define SMART_ERR_GAP (-3)           /* 'summary' with a run length not a multiple of report_gap:
+                                        the reference's np.reshape raises (structure.py:190) */
+#define SMART_ERR_CUDA (-4)          /* a CUDA runtime call failed; see smart_last_error() */
+#define SMART_ERR_NO_DEVICE (-5)
+
+/* Flags */
+#define SMART_FLAG_FORCE_GENERAL 0x1u /* always take the branch-faithful step (clamps, 95% river cap,
+                                         leak predicates); default: chosen per CTA from the parameters */
+#define SMART_FLAG_NO_TMA 0x2u        /* stage forcing with plain loads instead of cp.async.bulk */
+
+/*
+ * One batch of members.  Member m uses params[m][0..9] and catchment
+ *   c(m) = (n_catchments == 1) ? 0 : m / members_per_catchment.
+ */
+typedef struct smart_batch_desc {
+    /* ---- sizes */
+    int64_t n_members;              /* N >= 1 */
+    int64_t n_steps;                /* T: simulation steps of the main run (len(timeseries) - 1) */
+    int64_t n_warmup;               /* W = int(warm_up_days * 86400 / dt) (structure.py:88); 0 = none */
+    int32_t n_catchments;           /* C >= 1 */
+    int32_t members_per_catchment;  /* used when C > 1; N must equal C * members_per_catchment */
+    int32_t report_gap;             /* simulation steps per reporting step (structure.py:75) */
+    int32_t report_type;            /* SMART_REPORT_SUMMARY | SMART_REPORT_RAW */
+    uint32_t flags;                 /* SMART_FLAG_* */
+    int32_t reserved0;
+    double dt_sec;                  /* simulation time step in seconds */
+
+    /* ---- inputs */
+    const double *params;           /* [N][10] row-major, always binary64 */
+    const double *rain;             /* [T][C]  mm per step  (C == 1: plain [T]) */
+    const double *peva;             /* [T][C]  mm per step */
+    const double *area_m2;          /* [C] */
+    const double *obs;              /* [n_report][C], NaN = missing; NULL = no scoring */
+    const double *obs_stats;        /* [C][SMART_OBS_STATS] from smart_obs_stats(); required iff obs */
+    const double *initial_state;    /* optional [N][19]: start the MAIN run from these states
+                                       (no guess, no warm-up) -- the run_all_steps contract */
+
+    /* ---- initial-condition guess, structure.py:100-116 / :125-140 */
+    int32_t has_extra;              /* truthiness of the reference's `extra` dict */
+    int32_t reserved1;
+    double aar;                     /* extra['aar'] */
+    double ro_ratio;                /* extra['r-o_ratio'] */
+    double ro_split[5];             /* extra['r-o_split'] */
+    double gw_constraint;           /* settings 'gw_constraint'; 0 or NaN = off (montecarlo.py:71-74) */
+
+    /* ---- outputs (any may be NULL) */
+    void *discharge;                /* [n_report][ld_discharge] m3/s; double (f64 entry) or float (f32 entry) */
+    int64_t ld_discharge;           /* >= N */
+    double *scores;                 /* [N][8]; GW column is NaN when the constraint is off */
+    double *gw;                     /* [N] groundwater share of runoff (structure.py:191, :194-195) */
+    double *last_state;             /* [N][19] state after the last step (structure.py:197) */
+
+    /* ---- best member (optional): arg-max (best_sign > 0) or arg-min (< 0) of scores column
+     *      best_column over the batch, reduced with warp shuffles in the same pass */
+    int32_t best_column;
+    int32_t best_sign;              /* 0 = off */
+    double *best_score;             /* [1] */
+    int64_t *best_index;            /* [1] */
+    void *workspace;                /* smart_batch_workspace_bytes() bytes when best_sign != 0 */
+} smart_batch_desc;
+
+int smart_version(void);
+const char *smart_last_error(void);
+
+/* n_report implied by a descriptor: T/gap (summary) or ceil(T/gap) (raw). */
+int64_t smart_batch_n_report(const smart_batch_desc *d);
+size_t smart_batch_workspace_bytes(const smart_batch_desc *d);
+
+/* Per-catchment observation statistics used by the fused scores (device pointers). */
+int smart_obs_stats(const double *obs, int64_t n_report, int32_t n_catchments, double *stats, void *stream);
+
+/* The hot path.  FP64 state / FP32 state (scores are always accumulated in binary64). */
+int smart_batch_run_f64(const smart_batch_desc *d, void *stream);
+int smart_batch_run_f32(const smart_batch_desc *d, void *stream);
+
+/*
+ * Same, with HOST pointers everywhere in *d (workspace/obs_stats ignored: handled inside).
+ * Allocates device buffers, copies in, runs, copies out, synchronises.  precision: 64 | 32.
+ */
+int smart_batch_run_host(const smart_batch_desc *d, int precision, int device);
+
+/*
+ * Drop-in for smartcpp.allsteps (structure.py:118-121, :143-146), host pointers:
+ * discharge_out[length/gap | ceil(length/gap)], gw_out[1], last_out[19].
+ */
+int smart_allsteps_host(double area_m2, double delta_sec, int64_t length_simu,
+                        const double *nd_rain, const double *nd_peva,
+                        const double *nd_parameters, const double *nd_initial,
+                        int32_t report_type, int32_t report_gap,
+                        double *discharge_out, double *gw_out, double *last_out, int device);
+
+/*
+ * Measurement aid: register-resident dependent-chain DFMA (fp64) or FFMA (fp32) loop,
+ * `chains` independent chains per thread, `iters` FMAs per chain.  out[blocks*threads].
+ * FMA count = blocks * threads * chains * iters.  Used by bench.py to measure the FP64/FP32
+ * pipe peak that the roofline fraction is quoted against.
+ */
+int smart_fma_peak_probe(int precision, int blocks, int threads, int64_t iters, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMART_B200_H */

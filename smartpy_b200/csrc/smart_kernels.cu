@@ -1,0 +1,822 @@
+// smart_kernels.cu -- B200 (sm_100a) kernels and the C ABI of include/smart_b200.h.
+//
+// One thread = one member (parameter set x catchment).  The member's twelve stores live in
+// registers for the whole run; the thread walks the warm-up and then the main period
+// sequentially (the recurrence of smartpy/structure.py:181-187 is nonlinear in the state, so
+// time cannot be scanned).  Forcing is staged chunk by chunk into shared memory -- with 1-D
+// TMA bulk copies (cp.async.bulk + mbarrier, double buffered) for a single catchment, with
+// coalesced [t][catchment] tile loads for multi-catchment batches -- and broadcast to every
+// member of the CTA.  Reporting (structure.py:188-195) and the objective functions
+// (smartpy/montecarlo/montecarlo.py:193-209) are fused into the same pass: discharge goes
+// out as coalesced [t_report][member] stores, or not at all when only scores are wanted.
+#include "smart_b200.h"
+#include "smart_step.cuh"
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace {
+
+using namespace smart;
+
+constexpr int kBlock = 128;        // members per CTA
+constexpr int kChunkSingle = 512;  // forcing steps per smem stage, single catchment
+constexpr int kAccSlots = 6;       // per-thread binary64 accumulators parked in smem
+constexpr int kSmemHeader = 128;   // two mbarriers, padded
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define SMART_CUDA(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            return fail(SMART_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
+    } while (0)
+
+struct KArgs {
+    const double *params, *rain, *peva, *area, *obs, *obs_stats, *initial_state;
+    void *discharge;
+    double *scores, *gw, *last_state;
+    double *blk_best_score;
+    long long *blk_best_index;
+    long long N, T, W, ld_q;
+    int C, mpc, gap, report_type;
+    int chunk, kc, use_tma, force_general;
+    int has_extra, best_col, best_sign, first_report;
+    double dt, aar_ro, split[5], gw_constraint;
+};
+
+// ------------------------------------------------------------------ PTX helpers (TMA 1-D bulk + mbarrier)
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    // try_wait suspends in hardware up to a time limit; the bound only turns a lost copy
+    // into a trap instead of a hung GPU.
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+
+// ------------------------------------------------------------------ the time loop
+template <typename R, bool kGeneral, bool kFluxes>
+__device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
+                                             unsigned char *smem_raw, long long m, bool active, int c, int col,
+                                             int c_base, double area, double &gw_out, StepOut<R> &o)
+{
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    const int tile = a.chunk * a.kc;
+    double *s_rain = reinterpret_cast<double *>(smem_raw + kSmemHeader);   // [2][tile]
+    double *s_peva = s_rain + 2 * tile;                                   // [2][tile]
+    double *s_acc = s_peva + 2 * tile;                                    // [kAccSlots][kBlock]
+    const int tid = threadIdx.x;
+    double &A = s_acc[0 * kBlock + tid];      // sum (s - ebar)
+    double &B = s_acc[1 * kBlock + tid];      // sum (s - ebar)^2
+    double &Cc = s_acc[2 * kBlock + tid];     // sum (s - ebar)(e - ebar)
+    double &E = s_acc[3 * kBlock + tid];      // sum (s - e)^2
+    double &GN = s_acc[4 * kBlock + tid];     // sum (Q_sgw + Q_dgw)
+    double &GD = s_acc[5 * kBlock + tid];     // sum of the five pathway flows
+
+    const int chunk = a.chunk, kc = a.kc;
+    const long long nWc = (a.W + chunk - 1) / chunk;
+    const long long nMc = (a.T + chunk - 1) / chunk;
+    const long long nTot = nWc + nMc;
+    const bool summary = a.report_type == SMART_REPORT_SUMMARY;
+    const double ebar = a.obs ? a.obs_stats[c * SMART_OBS_STATS + 2] : 0.0;
+    const R qscale = static_cast<R>(area / (1e3 * a.dt));          // mm per step -> m3/s
+    const R mean_scale = static_cast<R>(area / (1e3 * a.dt) / static_cast<double>(a.gap));
+
+    auto chunk_span = [&](long long ci, long long &t0, int &n) {
+        if (ci < nWc) {
+            t0 = ci * chunk;
+            n = static_cast<int>(min(static_cast<long long>(chunk), a.W - t0));
+        } else {
+            t0 = (ci - nWc) * chunk;
+            n = static_cast<int>(min(static_cast<long long>(chunk), a.T - t0));
+        }
+    };
+    // TMA producer (one thread): even element counts go through cp.async.bulk (16-byte
+    // granules); an odd tail element is placed with a plain store BEFORE the releasing arrive.
+    auto tma_issue = [&](long long ci) {
+        long long t0;
+        int n;
+        chunk_span(ci, t0, n);
+        const int b = static_cast<int>(ci & 1);
+        double *dr = s_rain + b * tile, *dp = s_peva + b * tile;
+        const int n_even = n & ~1;
+        if (n & 1) {
+            dr[n - 1] = a.rain[t0 + n - 1];
+            dp[n - 1] = a.peva[t0 + n - 1];
+        }
+        mbar_arrive_expect_tx(&full[b], 2u * n_even * 8u);
+        if (n_even) {
+            tma_bulk_g2s(dr, a.rain + t0, n_even * 8u, &full[b]);
+            tma_bulk_g2s(dp, a.peva + t0, n_even * 8u, &full[b]);
+        }
+    };
+
+    int countdown = 0x7fffffff;   // never fires during the warm-up
+    long long r = 0;
+    R acc = R(0), agw = R(0), aall = R(0);
+    o.q_riv = o.q_gw = o.q_all = R(0);
+    o.aeva = o.q_ove = o.q_dra = o.q_int = o.q_sgw = o.q_dgw = R(0);
+
+    if (a.use_tma && tid == 0) tma_issue(0);
+
+    for (long long ci = 0; ci < nTot; ++ci) {
+        const int b = static_cast<int>(ci & 1);
+        long long t0;
+        int n;
+        chunk_span(ci, t0, n);
+        if (a.use_tma) {
+            if (tid == 0 && ci + 1 < nTot) tma_issue(ci + 1);
+            mbar_wait(&full[b], static_cast<uint32_t>((ci >> 1) & 1));
+        } else {
+            // coalesced tile load: rows t0..t0+n, columns c_base..c_base+kc of [T][C]
+            for (int idx = tid; idx < n * kc; idx += kBlock) {
+                const int row = idx / kc, cc = idx - row * kc;
+                const int cg = c_base + cc;
+                const bool ok = cg < a.C;
+                const long long g = (t0 + row) * static_cast<long long>(a.C) + cg;
+                s_rain[b * tile + idx] = ok ? a.rain[g] : 0.0;
+                s_peva[b * tile + idx] = ok ? a.peva[g] : 0.0;
+            }
+            __syncthreads();
+        }
+        if (ci == nWc) {   // the main run starts here (structure.py:143-146)
+            countdown = a.first_report;
+            r = 0;
+            acc = agw = aall = R(0);
+            A = B = Cc = E = GN = GD = 0.0;
+        }
+        const double *fr = s_rain + b * tile + col;
+        const double *fp = s_peva + b * tile + col;
+        for (int i = 0; i < n; ++i) {
+            smart_step<R, kGeneral, kFluxes>(s, p, fr[i * kc], fp[i * kc], o);
+            acc += o.q_riv;
+            agw += o.q_gw;
+            aall += o.q_all;
+            if (--countdown == 0) {
+                countdown = a.gap;
+                R sval;
+                if (summary) {
+                    sval = acc * mean_scale;                 // structure.py:190
+                } else {
+                    sval = o.q_riv * qscale;                 // structure.py:193
+                    agw = o.q_gw;                            // :194-195 sample the same rows
+                    aall = o.q_all;
+                }
+                GN += static_cast<double>(agw);
+                GD += static_cast<double>(aall);
+                acc = agw = aall = R(0);
+                if (a.discharge != nullptr && active) static_cast<R *>(a.discharge)[r * a.ld_q + m] = sval;
+                if (a.obs != nullptr) {
+                    const double e = __ldg(&a.obs[r * a.C + c]);
+                    if (e == e) {                            // montecarlo.py:195-196 NaN mask
+                        const double ds = static_cast<double>(sval) - ebar;
+                        const double de = e - ebar;
+                        const double df = ds - de;
+                        A += ds;
+                        B = fma(ds, ds, B);
+                        Cc = fma(ds, de, Cc);
+                        E = fma(df, df, E);
+                    }
+                }
+                ++r;
+            }
+        }
+        __syncthreads();   // every thread is done with stage b before it is refilled
+    }
+    gw_out = GN / GD;
+}
+
+template <typename R, bool kGeneral, bool kFluxes>
+__device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
+                                           long long m, bool active, int c, int col, int c_base, double area)
+{
+    const double T = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
+    const double SK = par[6], FK = par[7], GK = par[8], RK = par[9];
+    MemberPar<R> p;
+    p.Td = T;
+    p.C = static_cast<R>(C);
+    p.D = static_cast<R>(D);
+    p.omD = static_cast<R>(1.0 - D);
+    p.Hz = static_cast<R>(H / Z);
+    p.Sz = static_cast<R>(S / Z);
+    p.z = static_cast<R>(Z / 6.0);
+    p.r_sk = static_cast<R>(a.dt / (SK * 3600.0));
+    p.r_fk = static_cast<R>(a.dt / (FK * 3600.0));
+    p.r_gk = static_cast<R>(a.dt / (GK * 3600.0));
+    p.r_rk = static_cast<R>(a.dt / (RK * 3600.0));
+
+    // initial conditions in m3 exactly as the reference writes them, then to mm
+    const double to_mm = 1e3 / area;
+    double v[12];
+    if (a.initial_state != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) v[k] = a.initial_state[m * SMART_N_VARS + 7 + k];
+    } else {
+        const double kk[5] = {SK, SK, FK, GK, GK};
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            v[k] = a.has_extra ? a.aar_ro * a.split[k] / 1000 * area / 8766 * kk[k] : 0.0;   // structure.py:100-110
+        v[11] = a.has_extra ? a.aar_ro / 1000 * area / 8766 * RK : 0.0;                         // :111-112
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[5 + k] = (Z / 12) / 1000 * area;                          // :115-116
+    }
+    MemberState<R> s;
+    s.ove = static_cast<R>(v[0] * to_mm);
+    s.dra = static_cast<R>(v[1] * to_mm);
+    s.itf = static_cast<R>(v[2] * to_mm);
+    s.sgw = static_cast<R>(v[3] * to_mm);
+    s.dgw = static_cast<R>(v[4] * to_mm);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(v[5 + k] * to_mm);
+    s.riv = static_cast<R>(v[11] * to_mm);
+    if (!kGeneral) {   // same routing constant => one linear reservoir
+        s.ove = s.ove + s.dra;
+        s.sgw = s.sgw + s.dgw;
+        s.dra = s.dgw = R(0);
+    }
+
+    double gw = 0.0;
+    StepOut<R> o;
+    run_timeline<R, kGeneral, kFluxes>(a, s, p, smem_raw, m, active, c, col, c_base, area, gw, o);
+
+    // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
+    double *s_acc = reinterpret_cast<double *>(smem_raw + kSmemHeader) + 4 * a.chunk * a.kc;
+    const int tid = threadIdx.x;
+    double target = -CUDART_INF;
+    if (a.obs != nullptr) {
+        const double *st = a.obs_stats + c * SMART_OBS_STATS;
+        const double n = st[0], sum_e = st[1], ebar = st[2], sde = st[3], sse = st[4];
+        const double A = s_acc[0 * kBlock + tid], B = s_acc[1 * kBlock + tid];
+        const double Cc = s_acc[2 * kBlock + tid], E = s_acc[3 * kBlock + tid];
+        const double var_s = B - A * A / n;           // n * variance of the simulation
+        const double var_e = sse - sde * sde / n;     // n * variance of the observations
+        const double cov = Cc - A * sde / n;
+        double sc[SMART_N_SCORES];
+        sc[0] = 1.0 - E / sse;                                    // NSE
+        sc[2] = cov / sqrt(var_s * var_e);                        // KGEc (Pearson r)
+        sc[3] = sqrt(var_s / var_e);                              // KGEa
+        sc[4] = (A + n * ebar) / sum_e;                           // KGEb
+        sc[1] = 1.0 - sqrt((sc[2] - 1.0) * (sc[2] - 1.0) + (sc[3] - 1.0) * (sc[3] - 1.0) +
+                           (sc[4] - 1.0) * (sc[4] - 1.0));        // KGE
+        sc[5] = 100.0 * ((A - sde) / sum_e);                      // PBias
+        sc[6] = sqrt(E / n);                                      // RMSE
+        const bool gw_on = a.gw_constraint == a.gw_constraint && a.gw_constraint != 0.0;
+        sc[7] = gw_on ? ((a.gw_constraint - 0.1 <= gw && gw <= a.gw_constraint + 0.1) ? 1.0 : 0.0)
+                      : CUDART_NAN;                               // objfunctions.py:20-24
+        if (a.scores != nullptr && active) {
+#pragma unroll
+            for (int k = 0; k < SMART_N_SCORES; ++k) a.scores[m * SMART_N_SCORES + k] = sc[k];
+        }
+        if (a.best_sign != 0 && active) {
+            double t = sc[0];
+#pragma unroll
+            for (int k = 1; k < SMART_N_SCORES; ++k) t = (a.best_col == k) ? sc[k] : t;
+            t = a.best_sign > 0 ? t : -t;
+            target = (t == t) ? t : -CUDART_INF;
+        }
+    }
+    if (a.gw != nullptr && active) a.gw[m] = gw;
+    if (kFluxes && a.last_state != nullptr && active) {
+        // the 7 fluxes of the last step in m3/s, the 12 states back in m3 (structure.py:259-264)
+        double *ls = a.last_state + m * SMART_N_VARS;
+        const double to_m3 = area / 1e3;
+        const double to_flux = area / (1e3 * a.dt);
+        ls[0] = static_cast<double>(o.aeva) * to_flux;
+        ls[1] = static_cast<double>(o.q_ove) * to_flux;
+        ls[2] = static_cast<double>(o.q_dra) * to_flux;
+        ls[3] = static_cast<double>(o.q_int) * to_flux;
+        ls[4] = static_cast<double>(o.q_sgw) * to_flux;
+        ls[5] = static_cast<double>(o.q_dgw) * to_flux;
+        ls[6] = static_cast<double>(o.q_riv) * to_flux;
+        ls[7] = static_cast<double>(s.ove) * to_m3;
+        ls[8] = static_cast<double>(s.dra) * to_m3;
+        ls[9] = static_cast<double>(s.itf) * to_m3;
+        ls[10] = static_cast<double>(s.sgw) * to_m3;
+        ls[11] = static_cast<double>(s.dgw) * to_m3;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ls[12 + k] = static_cast<double>(s.ly[k]) * to_m3;
+        ls[18] = static_cast<double>(s.riv) * to_m3;
+    }
+    if (a.best_sign != 0) {
+        // arg-max over the CTA with warp shuffles; ties go to the lower member index
+        long long idx = active ? m : 0x7fffffffffffffffLL;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ot = __shfl_xor_sync(0xffffffffu, target, off);
+            const long long oi = __shfl_xor_sync(0xffffffffu, idx, off);
+            if (ot > target || (ot == target && oi < idx)) {
+                target = ot;
+                idx = oi;
+            }
+        }
+        __syncthreads();   // s_acc is free to reuse now
+        long long *s_idx = reinterpret_cast<long long *>(s_acc + kBlock);
+        if ((tid & 31) == 0) {
+            s_acc[tid >> 5] = target;
+            s_idx[tid >> 5] = idx;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kBlock / 32; ++w) {
+                const double ot = s_acc[w];
+                const long long oi = s_idx[w];
+                if (ot > target || (ot == target && oi < idx)) {
+                    target = ot;
+                    idx = oi;
+                }
+            }
+            a.blk_best_score[blockIdx.x] = target;
+            a.blk_best_index[blockIdx.x] = idx;
+        }
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kBlock) smart_batch_kernel(const KArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const long long m_raw = static_cast<long long>(blockIdx.x) * kBlock + tid;
+    const bool active = m_raw < a.N;
+    const long long m = active ? m_raw : a.N - 1;   // tail threads shadow the last member, store nothing
+
+    const bool multi = a.C > 1;
+    const int c = multi ? static_cast<int>(m / a.mpc) : 0;
+    const int c_base = multi ? static_cast<int>((static_cast<long long>(blockIdx.x) * kBlock) / a.mpc) : 0;
+    const int col = c - c_base;
+    const double area = a.area[c];
+
+    if (a.use_tma) {
+        uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+        if (tid == 0) {
+            mbar_init(&full[0], 1);
+            mbar_init(&full[1], 1);
+            mbar_fence_init();
+        }
+    }
+
+    double par[SMART_N_PARAMS];
+#pragma unroll
+    for (int k = 0; k < SMART_N_PARAMS; ++k) par[k] = a.params[m * SMART_N_PARAMS + k];
+
+    // The merged form is exact only when no clamp, cap or leak predicate can fire:
+    // every routing constant >= dt, inflows >= 0 (0 <= D <= 1, 0 <= H < 1), s' < 1.
+    const double dt = a.dt;
+    bool fast_ok = par[6] * 3600.0 >= dt && par[7] * 3600.0 >= dt && par[8] * 3600.0 >= dt &&
+                   par[9] * 3600.0 >= dt && par[4] >= 0.0 && par[4] <= 0.5 && par[5] > 0.0 &&
+                   par[3] >= 0.0 && par[3] <= 1.0 && par[2] >= 0.0 && par[2] <= 0.99 && par[0] >= 0.0;
+    fast_ok = fast_ok && !a.force_general && a.last_state == nullptr && a.initial_state == nullptr;
+    const int need_general = __syncthreads_or(fast_ok ? 0 : 1);   // also orders the mbarrier init
+
+    if (a.last_state != nullptr)
+        run_member<R, true, true>(a, smem_raw, par, m, active, c, col, c_base, area);
+    else if (need_general)
+        run_member<R, true, false>(a, smem_raw, par, m, active, c, col, c_base, area);
+    else
+        run_member<R, false, false>(a, smem_raw, par, m, active, c, col, c_base, area);
+}
+
+__global__ void best_finalize_kernel(const double *blk_score, const long long *blk_index, int n_blocks, int sign,
+                                     double *best_score, long long *best_index)
+{
+    double t = -CUDART_INF;
+    long long idx = 0x7fffffffffffffffLL;
+    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) {
+        const double ot = blk_score[i];
+        const long long oi = blk_index[i];
+        if (ot > t || (ot == t && oi < idx)) {
+            t = ot;
+            idx = oi;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ot = __shfl_xor_sync(0xffffffffu, t, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (ot > t || (ot == t && oi < idx)) {
+            t = ot;
+            idx = oi;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (best_score) *best_score = sign > 0 ? t : -t;
+        if (best_index) *best_index = idx;
+    }
+}
+
+// One CTA per catchment; fixed-order tree so the statistics are run-to-run deterministic.
+__global__ void obs_stats_kernel(const double *obs, long long n_report, int C, double *stats)
+{
+    __shared__ double sh[3][256];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    double n = 0.0, se = 0.0;
+    for (long long r = tid; r < n_report; r += 256) {
+        const double e = obs[r * C + c];
+        if (e == e) {
+            n += 1.0;
+            se += e;
+        }
+    }
+    sh[0][tid] = n;
+    sh[1][tid] = se;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) {
+            sh[0][tid] += sh[0][tid + off];
+            sh[1][tid] += sh[1][tid + off];
+        }
+        __syncthreads();
+    }
+    n = sh[0][0];
+    se = sh[1][0];
+    const double ebar = se / n;
+    __syncthreads();
+    double sd = 0.0, ss = 0.0;
+    for (long long r = tid; r < n_report; r += 256) {
+        const double e = obs[r * C + c];
+        if (e == e) {
+            const double de = e - ebar;
+            sd += de;
+            ss = fma(de, de, ss);
+        }
+    }
+    sh[1][tid] = sd;
+    sh[2][tid] = ss;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (tid < off) {
+            sh[1][tid] += sh[1][tid + off];
+            sh[2][tid] += sh[2][tid + off];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        double *st = stats + static_cast<long long>(c) * SMART_OBS_STATS;
+        st[0] = n;
+        st[1] = se;
+        st[2] = ebar;
+        st[3] = sh[1][0];
+        st[4] = sh[2][0];
+        st[5] = 0.0;
+    }
+}
+
+template <typename R, int kChains>
+__global__ void fma_peak_kernel(long long iters, double *out)
+{
+    R x[kChains];
+    const R a = R(1.0) - R(1e-7) * R(threadIdx.x + 1), b = R(1e-7);
+#pragma unroll
+    for (int j = 0; j < kChains; ++j) x[j] = R(j + 1);
+    for (long long i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < kChains; ++j) x[j] = fma(x[j], a, b);
+    }
+    R sum = R(0);
+#pragma unroll
+    for (int j = 0; j < kChains; ++j) sum += x[j];
+    out[static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x] = static_cast<double>(sum);
+}
+
+// ------------------------------------------------------------------ host side
+int64_t n_report_of(const smart_batch_desc *d)
+{
+    if (d->report_gap <= 0) return 0;
+    return d->report_type == SMART_REPORT_SUMMARY ? d->n_steps / d->report_gap
+                                                  : (d->n_steps + d->report_gap - 1) / d->report_gap;
+}
+
+int n_blocks_of(const smart_batch_desc *d) { return static_cast<int>((d->n_members + kBlock - 1) / kBlock); }
+
+int validate(const smart_batch_desc *d, bool host_mode = false)
+{
+    if (!d) return fail(SMART_ERR_BAD_ARG, "descriptor is NULL");
+    if (d->n_members < 1 || d->n_steps < 1 || d->n_steps >= 0x7fffffffLL || d->n_warmup < 0)
+        return fail(SMART_ERR_BAD_ARG, "n_members, n_steps must be >= 1 (n_steps < 2^31), n_warmup >= 0");
+    if (d->n_members > 0x7fffffffLL * kBlock) return fail(SMART_ERR_BAD_ARG, "n_members too large for one launch");
+    if (d->n_catchments < 1) return fail(SMART_ERR_BAD_ARG, "n_catchments must be >= 1");
+    if (d->n_catchments > 1 &&
+        (d->members_per_catchment < 1 ||
+         static_cast<int64_t>(d->members_per_catchment) * d->n_catchments != d->n_members))
+        return fail(SMART_ERR_BAD_ARG, "n_members must equal n_catchments * members_per_catchment");
+    if (d->report_type != SMART_REPORT_SUMMARY && d->report_type != SMART_REPORT_RAW)
+        return fail(SMART_ERR_BAD_ARG, "Reporting type unknown (1 = summary, 2 = raw)");   // structure.py:70
+    if (d->report_gap < 1) return fail(SMART_ERR_BAD_ARG, "report_gap must be >= 1");
+    if (!(d->dt_sec > 0.0)) return fail(SMART_ERR_BAD_ARG, "dt_sec must be > 0");
+    if (!d->params || !d->rain || !d->peva || !d->area_m2)
+        return fail(SMART_ERR_BAD_ARG, "params, rain, peva and area_m2 are required");
+    if (d->obs && !d->obs_stats && !host_mode) return fail(SMART_ERR_BAD_ARG, "obs given without obs_stats");
+    if (d->n_warmup > d->n_steps)   // structure.py:90-95
+        return fail(SMART_ERR_WARMUP_TOO_LONG,
+                    "The warm-up duration cannot exceed the length of the simulation period");
+    if (d->report_type == SMART_REPORT_SUMMARY) {   // np.reshape(-1, gap) at structure.py:190
+        if (d->n_steps % d->report_gap != 0)
+            return fail(SMART_ERR_GAP, "cannot reshape the simulation into (-1, report_gap)");
+        if (!d->initial_state && d->n_warmup % d->report_gap != 0)
+            return fail(SMART_ERR_GAP, "cannot reshape the warm-up run into (-1, report_gap)");
+    }
+    if (d->discharge && d->ld_discharge < d->n_members)
+        return fail(SMART_ERR_BAD_ARG, "ld_discharge must be >= n_members");
+    if (d->best_sign != 0) {
+        if (!d->obs || (!d->workspace && !host_mode))
+            return fail(SMART_ERR_BAD_ARG, "best member needs obs and workspace");
+        if (d->best_column < 0 || d->best_column >= SMART_N_SCORES)
+            return fail(SMART_ERR_BAD_ARG, "best_column out of range");
+    }
+    return SMART_OK;
+}
+
+template <typename R>
+int launch(const smart_batch_desc *d, cudaStream_t stream)
+{
+    int rc = validate(d);
+    if (rc) return rc;
+    KArgs a;
+    memset(&a, 0, sizeof a);
+    a.params = d->params;
+    a.rain = d->rain;
+    a.peva = d->peva;
+    a.area = d->area_m2;
+    a.obs = d->obs;
+    a.obs_stats = d->obs_stats;
+    a.initial_state = d->initial_state;
+    a.discharge = d->discharge;
+    a.scores = d->scores;
+    a.gw = d->gw;
+    a.last_state = d->last_state;
+    a.N = d->n_members;
+    a.T = d->n_steps;
+    a.W = d->initial_state ? 0 : d->n_warmup;
+    a.ld_q = d->ld_discharge;
+    a.C = d->n_catchments;
+    a.mpc = d->n_catchments > 1 ? d->members_per_catchment : 1;
+    a.gap = d->report_gap;
+    a.report_type = d->report_type;
+    a.has_extra = d->has_extra;
+    a.dt = d->dt_sec;
+    a.aar_ro = d->aar * d->ro_ratio;   // (extra['aar'] * extra['r-o_ratio']), structure.py:102
+    for (int k = 0; k < 5; ++k) a.split[k] = d->ro_split[k];
+    a.gw_constraint = d->gw_constraint;
+    a.force_general = (d->flags & SMART_FLAG_FORCE_GENERAL) ? 1 : 0;
+    a.best_col = d->best_column;
+    a.best_sign = d->best_sign;
+    // first reporting step of the main run, 1-based: [::-gap][::-1] counts back from the end
+    const int64_t n_rep = n_report_of(d);
+    a.first_report = static_cast<int>(d->n_steps - (n_rep - 1) * d->report_gap);
+
+    const int blocks = n_blocks_of(d);
+    if (a.C == 1) {
+        a.kc = 1;
+        a.chunk = kChunkSingle;
+        const bool aligned = (reinterpret_cast<uintptr_t>(d->rain) % 16 == 0) &&
+                             (reinterpret_cast<uintptr_t>(d->peva) % 16 == 0);
+        a.use_tma = (aligned && !(d->flags & SMART_FLAG_NO_TMA)) ? 1 : 0;
+    } else {
+        a.kc = (kBlock - 1) / a.mpc + 2;              // catchments one CTA can straddle
+        if (a.kc > a.C) a.kc = a.C;
+        int chunk = (24 * 1024) / (2 * 2 * 8 * a.kc);
+        chunk = chunk > 512 ? 512 : chunk;
+        chunk &= ~7;
+        if (chunk < 8) return fail(SMART_ERR_BAD_ARG, "members_per_catchment too small for one CTA tile");
+        a.chunk = chunk;
+        a.use_tma = 0;
+    }
+    if (d->best_sign != 0) {
+        a.blk_best_score = static_cast<double *>(d->workspace);
+        a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
+    }
+    const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(a.chunk) * a.kc + kAccSlots * kBlock);
+    smart_batch_kernel<R><<<blocks, kBlock, smem, stream>>>(a);
+    SMART_CUDA(cudaGetLastError());
+    if (d->best_sign != 0) {
+        best_finalize_kernel<<<1, 32, 0, stream>>>(a.blk_best_score, a.blk_best_index, blocks, d->best_sign,
+                                                   d->best_score, reinterpret_cast<long long *>(d->best_index));
+        SMART_CUDA(cudaGetLastError());
+    }
+    return SMART_OK;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int smart_version(void) { return SMART_B200_VERSION; }
+
+const char *smart_last_error(void) { return g_err.c_str(); }
+
+int64_t smart_batch_n_report(const smart_batch_desc *d) { return d ? n_report_of(d) : 0; }
+
+size_t smart_batch_workspace_bytes(const smart_batch_desc *d)
+{
+    if (!d || d->best_sign == 0) return 0;
+    return static_cast<size_t>(n_blocks_of(d)) * (sizeof(double) + sizeof(long long));
+}
+
+int smart_obs_stats(const double *obs, int64_t n_report, int32_t n_catchments, double *stats, void *stream)
+{
+    if (!obs || !stats || n_report < 1 || n_catchments < 1)
+        return fail(SMART_ERR_BAD_ARG, "smart_obs_stats: bad argument");
+    obs_stats_kernel<<<n_catchments, 256, 0, static_cast<cudaStream_t>(stream)>>>(obs, n_report, n_catchments, stats);
+    SMART_CUDA(cudaGetLastError());
+    return SMART_OK;
+}
+
+int smart_batch_run_f64(const smart_batch_desc *d, void *stream)
+{
+    return launch<double>(d, static_cast<cudaStream_t>(stream));
+}
+
+int smart_batch_run_f32(const smart_batch_desc *d, void *stream)
+{
+    return launch<float>(d, static_cast<cudaStream_t>(stream));
+}
+
+int smart_batch_run_host(const smart_batch_desc *h, int precision, int device)
+{
+    if (precision != 64 && precision != 32) return fail(SMART_ERR_BAD_ARG, "precision must be 64 or 32");
+    int rc = validate(h, true);
+    if (rc) return rc;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
+        return fail(SMART_ERR_NO_DEVICE, "no CUDA device: the SMART hot path has no CPU fallback");
+    SMART_CUDA(cudaSetDevice(device));
+    cudaStream_t st;
+    SMART_CUDA(cudaStreamCreate(&st));
+    struct StreamGuard {
+        cudaStream_t s;
+        ~StreamGuard() { cudaStreamDestroy(s); }
+    } guard{st};
+
+    const int64_t N = h->n_members, T = h->n_steps, C = h->n_catchments;
+    const int64_t n_rep = n_report_of(h);
+    const size_t q_elem = precision == 64 ? sizeof(double) : sizeof(float);
+    smart_batch_desc d = *h;
+    DevBuf params, rain, peva, area, obs, stats, init, q, scores, gw, last, ws, bs, bi;
+    auto up = [&](DevBuf &b, const void *src, size_t bytes, const void **dst) -> int {
+        SMART_CUDA(cudaMalloc(&b.p, bytes));
+        SMART_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+        *dst = b.p;
+        return SMART_OK;
+    };
+    if ((rc = up(params, h->params, sizeof(double) * N * SMART_N_PARAMS, (const void **)&d.params))) return rc;
+    if ((rc = up(rain, h->rain, sizeof(double) * T * C, (const void **)&d.rain))) return rc;
+    if ((rc = up(peva, h->peva, sizeof(double) * T * C, (const void **)&d.peva))) return rc;
+    if ((rc = up(area, h->area_m2, sizeof(double) * C, (const void **)&d.area_m2))) return rc;
+    if (h->initial_state &&
+        (rc = up(init, h->initial_state, sizeof(double) * N * SMART_N_VARS, (const void **)&d.initial_state)))
+        return rc;
+    if (h->obs) {
+        if ((rc = up(obs, h->obs, sizeof(double) * n_rep * C, (const void **)&d.obs))) return rc;
+        SMART_CUDA(cudaMalloc(&stats.p, sizeof(double) * C * SMART_OBS_STATS));
+        d.obs_stats = static_cast<double *>(stats.p);
+        if ((rc = smart_obs_stats(d.obs, n_rep, static_cast<int32_t>(C), static_cast<double *>(stats.p), st)))
+            return rc;
+    }
+    if (h->discharge) {
+        d.ld_discharge = N;
+        SMART_CUDA(cudaMalloc(&q.p, q_elem * n_rep * N));
+        d.discharge = q.p;
+    }
+    if (h->scores) {
+        SMART_CUDA(cudaMalloc(&scores.p, sizeof(double) * N * SMART_N_SCORES));
+        d.scores = static_cast<double *>(scores.p);
+    }
+    if (h->gw) {
+        SMART_CUDA(cudaMalloc(&gw.p, sizeof(double) * N));
+        d.gw = static_cast<double *>(gw.p);
+    }
+    if (h->last_state) {
+        SMART_CUDA(cudaMalloc(&last.p, sizeof(double) * N * SMART_N_VARS));
+        d.last_state = static_cast<double *>(last.p);
+    }
+    if (h->best_sign != 0) {
+        SMART_CUDA(cudaMalloc(&ws.p, smart_batch_workspace_bytes(h)));
+        SMART_CUDA(cudaMalloc(&bs.p, sizeof(double)));
+        SMART_CUDA(cudaMalloc(&bi.p, sizeof(long long)));
+        d.workspace = ws.p;
+        d.best_score = static_cast<double *>(bs.p);
+        d.best_index = static_cast<int64_t *>(bi.p);
+    }
+    rc = precision == 64 ? launch<double>(&d, st) : launch<float>(&d, st);
+    if (rc) return rc;
+    if (h->discharge) {
+        // host layout keeps the caller's leading dimension
+        SMART_CUDA(cudaMemcpy2DAsync(h->discharge, q_elem * h->ld_discharge, q.p, q_elem * N, q_elem * N, n_rep,
+                                     cudaMemcpyDeviceToHost, st));
+    }
+    if (h->scores)
+        SMART_CUDA(cudaMemcpyAsync(h->scores, scores.p, sizeof(double) * N * SMART_N_SCORES, cudaMemcpyDeviceToHost, st));
+    if (h->gw) SMART_CUDA(cudaMemcpyAsync(h->gw, gw.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (h->last_state)
+        SMART_CUDA(cudaMemcpyAsync(h->last_state, last.p, sizeof(double) * N * SMART_N_VARS, cudaMemcpyDeviceToHost, st));
+    if (h->best_sign != 0) {
+        if (h->best_score) SMART_CUDA(cudaMemcpyAsync(h->best_score, bs.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h->best_index) SMART_CUDA(cudaMemcpyAsync(h->best_index, bi.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    SMART_CUDA(cudaStreamSynchronize(st));
+    return SMART_OK;
+}
+
+int smart_allsteps_host(double area_m2, double delta_sec, int64_t length_simu, const double *nd_rain,
+                        const double *nd_peva, const double *nd_parameters, const double *nd_initial,
+                        int32_t report_type, int32_t report_gap, double *discharge_out, double *gw_out,
+                        double *last_out, int device)
+{
+    smart_batch_desc d;
+    memset(&d, 0, sizeof d);
+    d.n_members = 1;
+    d.n_steps = length_simu;
+    d.n_warmup = 0;
+    d.n_catchments = 1;
+    d.members_per_catchment = 1;
+    d.report_gap = report_gap;
+    d.report_type = report_type;
+    d.flags = SMART_FLAG_FORCE_GENERAL;
+    d.dt_sec = delta_sec;
+    d.params = nd_parameters;
+    d.rain = nd_rain;
+    d.peva = nd_peva;
+    d.area_m2 = &area_m2;
+    d.initial_state = nd_initial;
+    d.discharge = discharge_out;
+    d.ld_discharge = 1;
+    d.gw = gw_out;
+    d.last_state = last_out;
+    return smart_batch_run_host(&d, 64, device);
+}
+
+int smart_fma_peak_probe(int precision, int blocks, int threads, int64_t iters, double *out, void *stream)
+{
+    if (blocks < 1 || threads < 1 || threads > 1024 || iters < 1 || !out)
+        return fail(SMART_ERR_BAD_ARG, "smart_fma_peak_probe: bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == 64)
+        fma_peak_kernel<double, 8><<<blocks, threads, 0, st>>>(iters, out);
+    else if (precision == 32)
+        fma_peak_kernel<float, 8><<<blocks, threads, 0, st>>>(iters, out);
+    else
+        return fail(SMART_ERR_BAD_ARG, "precision must be 64 or 32");
+    SMART_CUDA(cudaGetLastError());
+    return SMART_OK;
+}
+
+}  // extern "C"

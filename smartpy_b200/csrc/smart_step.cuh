@@ -1,0 +1,194 @@
+// smart_step.cuh -- one SMART time step for one member, state held in registers.
+//
+// Restates smartpy/structure.py:267-503 of the reference (run_one_step_catchment +
+// run_one_step_river, glued at :200-264) with these deliberate changes of FORM (results
+// agree with the reference to ~1e-13 relative, see tests/test_gpu_parity.py):
+//   * every store is kept in millimetres over the catchment (V / area * 1e3) instead of m3,
+//     so the per-step m3<->mm conversions of :341-346, :424-457 disappear;
+//   * per-member constants are hoisted: h' = (H/Z) * tot, s' = (S/Z) * tot, r_x = dt / k_x;
+//   * s'^i by repeated multiplication instead of pow() (:382, :396), s'/i by reciprocal (:389);
+//   * the dead output Q_aeva (:424) is not computed.
+// The one true discontinuity of the model -- the wet/dry predicate `rain * T - peva >= 0`
+// (:353-359) -- is evaluated exactly as the reference does: a rounded binary64 multiply, then
+// a rounded subtract (no FMA contraction), in binary64 even in FP32 mode.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace smart {
+
+template <typename R>
+struct MemberPar {
+    double Td;            // T in binary64 for the wet/dry predicate
+    R C, D, omD;          // C, D, (1 - D)
+    R Hz, Sz;             // H / Z, S / Z
+    R z;                  // Z / 6
+    R r_sk, r_fk, r_gk, r_rk;   // dt / (k * 3600)
+};
+
+// mm-equivalent stores.  In the merged ("fast") form `ove` carries V_ove + V_dra and `sgw`
+// carries V_sgw + V_dgw (same routing constant => same linear reservoir), `dra`/`dgw` unused.
+template <typename R>
+struct MemberState {
+    R ly[6];
+    R ove, dra, itf, sgw, dgw;
+    R riv;
+};
+
+template <typename R>
+struct StepOut {
+    R q_riv;   // river outflow, mm per step
+    R q_gw;    // Q_sgw + Q_dgw, mm per step
+    R q_all;   // sum of the five pathway outflows, mm per step
+    // only filled when kFluxes (the run_all_steps / run_one_step contract wants all 19 columns)
+    R aeva, q_ove, q_dra, q_int, q_sgw, q_dgw;   // mm per step
+};
+
+template <typename R> __device__ __forceinline__ R inv_const(int i);
+template <> __device__ __forceinline__ double inv_const<double>(int i)
+{
+    return i == 0 ? 1.0 : i == 1 ? 0.5 : i == 2 ? (1.0 / 3.0) : i == 3 ? 0.25 : i == 4 ? 0.2 : (1.0 / 6.0);
+}
+template <> __device__ __forceinline__ float inv_const<float>(int i)
+{
+    return i == 0 ? 1.0f : i == 1 ? 0.5f : i == 2 ? (1.0f / 3.0f) : i == 3 ? 0.25f : i == 4 ? 0.2f : (1.0f / 6.0f);
+}
+
+// kGeneral = true : branch-faithful form -- five separate reservoirs with the >= 0 clamps
+//                   (:427-450), the 95 % river cap (:492-498) and the `leak < level`
+//                   predicates (:383, :390, :397).  Needed when dt > k for some store, when
+//                   S/Z*tot can reach 1, or when the caller wants the 19-vector back.
+// kGeneral = false: merged reservoirs, no clamps/cap/predicates -- valid exactly when none of
+//                   them can fire (decided per CTA in the kernel from the parameters).
+// kFluxes (needs kGeneral): also return actual evapotranspiration and the five pathway
+//                   outflows of this step (structure.py:424-447), for the 19-vector.
+template <typename R, bool kGeneral, bool kFluxes = false>
+__device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R> &p,
+                                           double rain, double peva, StepOut<R> &o)
+{
+    const R zero = R(0);
+    // structure.py:350 -- left-to-right sum of the six layer levels
+    R tot = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+
+    // structure.py:353-359 -- binary64, separately rounded
+    const double rain_c = __dmul_rn(rain, p.Td);
+    const double ex_d = __dsub_rn(rain_c, peva);
+
+    R in_ove = zero, in_dra = zero, in_int = zero, in_sgw = zero, in_dgw = zero;
+
+    if (ex_d >= 0.0) {
+        // ---- wet branch, structure.py:360-399
+        R ex = static_cast<R>(ex_d);
+        if (kFluxes) o.aeva = static_cast<R>(peva);   // :361
+        in_ove = (p.Hz * tot) * ex;                 // :363-364
+        ex = ex - in_ove;                           // :365
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {               // :367-374
+            const R space = p.z - s.ly[i];
+            const bool fits = ex <= space;
+            const R add = fits ? ex : space;
+            s.ly[i] = fits ? s.ly[i] + add : p.z;
+            ex = ex - add;
+        }
+        in_dra = p.D * ex;                          // :376
+        in_int = p.omD * ex;                        // :377
+        const R sp = p.Sz * tot;                    // :379 (start-of-step total)
+        R pw[6];
+        pw[0] = sp;
+        pw[1] = sp * sp;
+        pw[2] = pw[1] * sp;
+        pw[3] = pw[1] * pw[1];
+        pw[4] = pw[3] * sp;
+        pw[5] = pw[2] * pw[2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {               // :381-385 interflow leak, top down
+            const R leak = s.ly[i] * pw[i];
+            if (!kGeneral || leak < s.ly[i]) {
+                in_int += leak;
+                s.ly[i] -= leak;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {               // :388-392 shallow groundwater leak
+            const R leak = s.ly[i] * (i == 0 ? sp : sp * inv_const<R>(i));
+            if (!kGeneral || leak < s.ly[i]) {
+                in_sgw += leak;
+                s.ly[i] -= leak;
+            }
+        }
+#pragma unroll
+        for (int i = 5; i >= 0; --i) {              // :395-399 deep groundwater leak, bottom up
+            const R leak = s.ly[i] * pw[5 - i];
+            if (!kGeneral || leak < s.ly[i]) {
+                in_dgw += leak;
+                s.ly[i] -= leak;
+            }
+        }
+    } else {
+        // ---- dry branch, structure.py:400-419 (aeva is dead downstream and not tracked)
+        R d = static_cast<R>(-ex_d);
+        R aeva = static_cast<R>(rain_c);            // :408
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const R t = s.ly[i] - d;
+            const bool enough = !(t < zero);        // level >= deficit
+            if (kFluxes) aeva += enough ? d : s.ly[i];   // :412, :415
+            s.ly[i] = enough ? t : zero;
+            d = enough ? zero : p.C * (-t);
+        }
+        if (kFluxes) o.aeva = aeva;
+    }
+
+    if (kGeneral) {
+        // structure.py:427-450 -- outflow from the OLD storage, then update, then clamp
+        const R q_ove = s.ove * p.r_sk;
+        s.ove = s.ove + (in_ove - q_ove);
+        if (s.ove < zero) s.ove = zero;
+        const R q_dra = s.dra * p.r_sk;
+        s.dra = s.dra + (in_dra - q_dra);
+        if (s.dra < zero) s.dra = zero;
+        const R q_int = s.itf * p.r_fk;
+        s.itf = s.itf + (in_int - q_int);
+        if (s.itf < zero) s.itf = zero;
+        const R q_sgw = s.sgw * p.r_gk;
+        s.sgw = s.sgw + (in_sgw - q_sgw);
+        if (s.sgw < zero) s.sgw = zero;
+        const R q_dgw = s.dgw * p.r_gk;
+        s.dgw = s.dgw + (in_dgw - q_dgw);
+        if (s.dgw < zero) s.dgw = zero;
+        o.q_gw = q_sgw + q_dgw;
+        if (kFluxes) {
+            o.q_ove = q_ove;
+            o.q_dra = q_dra;
+            o.q_int = q_int;
+            o.q_sgw = q_sgw;
+            o.q_dgw = q_dgw;
+        }
+        const R q_in = (((q_ove + q_dra) + q_int) + q_sgw) + q_dgw;    // :254
+        o.q_all = q_in;
+        // structure.py:482-498
+        R q = s.riv * p.r_rk;
+        const R tmp = s.riv + (q_in - q);
+        if (tmp < zero) {
+            q = R(0.95) * (q_in + s.riv);
+            s.riv = s.riv + (q_in - q);
+        } else {
+            s.riv = tmp;
+        }
+        o.q_riv = q;
+    } else {
+        const R q_quick = s.ove * p.r_sk;
+        s.ove = (s.ove - q_quick) + (in_ove + in_dra);
+        const R q_int = s.itf * p.r_fk;
+        s.itf = (s.itf - q_int) + in_int;
+        const R q_gw = s.sgw * p.r_gk;
+        s.sgw = (s.sgw - q_gw) + (in_sgw + in_dgw);
+        o.q_gw = q_gw;
+        const R q_in = (q_quick + q_int) + q_gw;
+        o.q_all = q_in;
+        const R q = s.riv * p.r_rk;
+        s.riv = (s.riv - q) + q_in;
+        o.q_riv = q;
+    }
+}
+
+}  // namespace smart

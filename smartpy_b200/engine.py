@@ -1,0 +1,252 @@
+"""Batch engine: device-resident forcing/observations + one kernel launch per batch of members.
+
+This is the thin host layer between the drop-in API (``smart.py``, ``montecarlo``) and the C
+ABI (``include/smart_b200.h``).  PyTorch is used only as plumbing: device memory, pinned
+staging buffers and the CUDA stream handle that is passed to the library.
+
+Replaces, for a whole batch at once, the per-sample call chain of the reference:
+``MonteCarlo.simulation`` -> ``SMART.simulate`` -> ``structure.run`` -> ``run_all_steps``
+(smartpy/montecarlo/montecarlo.py:179-186, smartpy/smart.py:204-210,
+smartpy/structure.py:30-197) and ``MonteCarlo.objectivefunction`` (montecarlo.py:193-209).
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _native
+
+SCORE_NAMES = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("smartpy_b200 needs a CUDA device (B200, sm_100a): there is no CPU fallback.")
+    return torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def report_type_of(report):
+    """structure.py:65-70."""
+    if report == 'summary':
+        return _native.REPORT_SUMMARY
+    if report == 'raw':
+        return _native.REPORT_RAW
+    raise Exception('Reporting type \'{}\' unknown.'.format(report))
+
+
+class BatchEngine(object):
+    """Holds one forcing set on the device and runs batches of members through the kernel.
+
+    rain, peva : array [T] (one catchment) or [T, C] (C catchments, read as [t][catchment])
+    area_m2    : float or array [C]
+    obs        : optional array [n_report] or [n_report, C], NaN = missing
+    """
+
+    def __init__(self, rain, peva, area_m2, delta_sec, report_gap, obs=None, extra=None,
+                 warm_up_steps=0, report='summary', gw_constraint=None,
+                 members_per_catchment=None, precision='f64', device=None, flags=0):
+        torch = _torch()
+        self.lib = _native.load()
+        self.device = _require_cuda(device)
+        if precision not in ('f64', 'f32'):
+            raise ValueError("precision must be 'f64' or 'f32'")
+        self.precision = precision
+        self.flags = int(flags)
+        self.report_type = report_type_of(report)
+        self.report_gap = int(report_gap)
+        self.delta_sec = float(delta_sec)
+        self.warm_up_steps = int(warm_up_steps)
+        self.extra = extra
+        self.gw_constraint = gw_constraint
+
+        rain = torch.as_tensor(np.ascontiguousarray(rain, dtype=np.float64) if not torch.is_tensor(rain) else rain)
+        peva = torch.as_tensor(np.ascontiguousarray(peva, dtype=np.float64) if not torch.is_tensor(peva) else peva)
+        if rain.shape != peva.shape:
+            raise ValueError("rain and peva must have the same shape")
+        self.n_steps = int(rain.shape[0])
+        self.n_catchments = 1 if rain.dim() == 1 else int(rain.shape[1])
+        self.members_per_catchment = int(members_per_catchment) if members_per_catchment else 0
+        self.rain = rain.to(self.device, torch.float64).contiguous()
+        self.peva = peva.to(self.device, torch.float64).contiguous()
+        area = np.atleast_1d(np.asarray(area_m2, dtype=np.float64))
+        if area.shape != (self.n_catchments,):
+            raise ValueError("area_m2 must have one value per catchment")
+        self.area = torch.from_numpy(area).to(self.device)
+
+        if self.report_type == _native.REPORT_SUMMARY:
+            self.n_report = self.n_steps // self.report_gap
+        else:
+            self.n_report = -(-self.n_steps // self.report_gap)
+
+        self.obs = None
+        self.obs_stats = None
+        if obs is not None:
+            obs_t = torch.as_tensor(np.ascontiguousarray(obs, dtype=np.float64) if not torch.is_tensor(obs) else obs)
+            if obs_t.shape[0] != self.n_report:
+                raise ValueError("obs must have n_report = {} rows".format(self.n_report))
+            self.obs = obs_t.to(self.device, torch.float64).contiguous()
+            self.obs_stats = torch.empty((self.n_catchments, _native.OBS_STATS), dtype=torch.float64,
+                                         device=self.device)
+            with torch.cuda.device(self.device):
+                rc = self.lib.smart_obs_stats(self.obs.data_ptr(), self.n_report, self.n_catchments,
+                                              self.obs_stats.data_ptr(),
+                                              torch.cuda.current_stream(self.device).cuda_stream)
+            _native.check(rc)
+
+    # ------------------------------------------------------------------ descriptor
+    def _desc(self, n_members):
+        d = _native.BatchDesc()
+        d.n_members = n_members
+        d.n_steps = self.n_steps
+        d.n_warmup = self.warm_up_steps
+        d.n_catchments = self.n_catchments
+        d.members_per_catchment = self.members_per_catchment if self.n_catchments > 1 else 1
+        d.report_gap = self.report_gap
+        d.report_type = self.report_type
+        d.flags = self.flags
+        d.dt_sec = self.delta_sec
+        d.rain = self.rain.data_ptr()
+        d.peva = self.peva.data_ptr()
+        d.area_m2 = self.area.data_ptr()
+        if self.extra:   # truthiness, as structure.py:100
+            d.has_extra = 1
+            d.aar = float(self.extra['aar'])
+            d.ro_ratio = float(self.extra['r-o_ratio'])
+            for k in range(5):
+                d.ro_split[k] = float(self.extra['r-o_split'][k])
+        gwc = self.gw_constraint
+        d.gw_constraint = float(gwc) if gwc else float('nan')   # truthiness, as montecarlo.py:71-74
+        return d
+
+    # ------------------------------------------------------------------ run
+    def run(self, params, discharge=False, scores=None, gw=True, last_state=False,
+            initial_state=None, best=None, out=None):
+        """Run every row of params[N, 10] (names order T,C,H,D,S,Z,SK,FK,GK,RK).
+
+        params may be a numpy array (copied host->device through pinned memory) or a CUDA
+        float64 tensor (used in place).  Returns a dict of device tensors:
+          'discharge' [n_report, N] (m3/s), 'scores' [N, 8], 'gw' [N], 'last_state' [N, 19],
+          'best' (score, index) -- only those requested.  Stream-ordered; nothing synchronises.
+        """
+        torch = _torch()
+        dev = self.device
+        if scores is None:
+            scores = self.obs is not None
+        if scores and self.obs is None:
+            raise Exception("scores requested but the engine has no observations")
+        if torch.is_tensor(params):
+            p_dev = params.to(dev, torch.float64).contiguous()
+        else:
+            p_host = np.ascontiguousarray(params, dtype=np.float64)
+            if p_host.ndim == 1:
+                p_host = p_host[None, :]
+            pinned = torch.from_numpy(p_host).pin_memory()
+            p_dev = pinned.to(dev, non_blocking=True)
+        if p_dev.dim() != 2 or p_dev.shape[1] != _native.N_PARAMS:
+            raise ValueError("params must be [N, 10]")
+        n = int(p_dev.shape[0])
+        d = self._desc(n)
+        d.params = p_dev.data_ptr()
+        keep = [p_dev]
+        res = {}
+        out = out or {}
+        qdtype = torch.float64 if self.precision == 'f64' else torch.float32
+        if discharge:
+            q = out.get('discharge')
+            if q is None:
+                q = torch.empty((self.n_report, n), dtype=qdtype, device=dev)
+            d.discharge = q.data_ptr()
+            d.ld_discharge = q.stride(0)
+            res['discharge'] = q
+        if scores or best:
+            d.obs = self.obs.data_ptr()
+            d.obs_stats = self.obs_stats.data_ptr()
+        if scores:
+            sc = out.get('scores')
+            if sc is None:
+                sc = torch.empty((n, _native.N_SCORES), dtype=torch.float64, device=dev)
+            d.scores = sc.data_ptr()
+            res['scores'] = sc
+        if gw:
+            g = out.get('gw')
+            if g is None:
+                g = torch.empty((n,), dtype=torch.float64, device=dev)
+            d.gw = g.data_ptr()
+            res['gw'] = g
+        if last_state:
+            ls = torch.empty((n, _native.N_VARS), dtype=torch.float64, device=dev)
+            d.last_state = ls.data_ptr()
+            res['last_state'] = ls
+        if initial_state is not None:
+            ini = torch.as_tensor(np.ascontiguousarray(initial_state, dtype=np.float64)
+                                  if not torch.is_tensor(initial_state) else initial_state)
+            ini = ini.reshape(-1, _native.N_VARS).to(dev, torch.float64).contiguous()
+            if ini.shape[0] != n:
+                raise ValueError("initial_state must be [N, 19]")
+            d.initial_state = ini.data_ptr()
+            keep.append(ini)
+        if best:
+            column, sign = best
+            d.best_column = SCORE_NAMES.index(column) if isinstance(column, str) else int(column)
+            d.best_sign = 1 if sign > 0 else -1
+            ws_bytes = self.lib.smart_batch_workspace_bytes(ctypes.byref(d))
+            ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.float64, device=dev)
+            bs = torch.empty(1, dtype=torch.float64, device=dev)
+            bi = torch.empty(1, dtype=torch.int64, device=dev)
+            d.workspace = ws.data_ptr()
+            d.best_score = bs.data_ptr()
+            d.best_index = bi.data_ptr()
+            keep.append(ws)
+            res['best'] = (bs, bi)
+        fn = self.lib.smart_batch_run_f64 if self.precision == 'f64' else self.lib.smart_batch_run_f32
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            rc = fn(ctypes.byref(d), stream.cuda_stream)
+        _native.check(rc)
+        for t in keep:   # keep inputs alive until the stream has consumed them
+            t.record_stream(stream)
+        return res
+
+    # steps one launch of n members walks through (warm-up + main), for throughput accounting
+    def member_steps(self, n_members):
+        return int(n_members) * (self.n_steps + self.warm_up_steps)
+
+
+def warm_up_length(warm_up_days, delta_sec):
+    """structure.py:88."""
+    return int(warm_up_days * 86400 / delta_sec)
+
+
+def fma_peak(precision=64, blocks=None, threads=256, iters=1 << 16, repeats=5, device=None):
+    """Measured FMA-pipe peak of the visible GPU in FMA instructions per second (per thread-op).
+
+    Runs the library's register-resident FMA probe and times it with CUDA events on the
+    launching stream.  Returns (fma_per_second, ms).
+    """
+    torch = _torch()
+    dev = _require_cuda(device)
+    lib = _native.load()
+    sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    blocks = blocks or sm * 8
+    out = torch.empty(blocks * threads, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    best = math.inf
+    with torch.cuda.device(dev):
+        for i in range(repeats + 1):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            _native.check(lib.smart_fma_peak_probe(precision, blocks, threads, iters, out.data_ptr(),
+                                                   stream.cuda_stream))
+            e1.record(stream)
+            e1.synchronize()
+            if i:
+                best = min(best, e0.elapsed_time(e1))
+    fmas = blocks * threads * 8 * iters
+    return fmas / (best * 1e-3), best

@@ -1,0 +1,302 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/smart_b200.h) against
+(a) outputs of the reference itself (tests/golden/*.npz) and (b) the CPU oracle on the same
+seeded inputs.
+
+Tolerances (BASELINE.json north_star): FP64 discharge within 1e-10 relative of the
+reference; FP32 mode NSE/KGE within 1e-5 absolute.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, EXTRA
+
+pytestmark = pytest.mark.gpu
+
+RTOL_Q = 1e-10      # north_star: FP64 discharge within 1e-10 relative
+ATOL_F32 = 1e-5     # north_star: FP32 NSE/KGE within 1e-5 absolute
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), 1e-300)
+    return float(np.max(np.abs(a - b) / den))
+
+
+def make_engine(c, report='summary', warm_up_days=365, extra=EXTRA, obs=True, gwc=0.12667, precision='f64',
+                flags=0, n_steps=None):
+    from smartpy_b200.engine import BatchEngine, warm_up_length
+    n = c.n_steps if n_steps is None else n_steps
+    return BatchEngine(c.rain[:n], c.peva[:n], c.area, c.dt, c.gap, obs=c.obs[:n // c.gap] if obs else None,
+                       extra=extra, warm_up_steps=warm_up_length(warm_up_days, c.dt) if warm_up_days else 0,
+                       report=report, gw_constraint=gwc, precision=precision, flags=flags)
+
+
+# ---------------------------------------------------------------- C1: the reference's own test configuration
+@pytest.mark.parametrize("tag,kw", [
+    ("summary", {}),
+    ("raw", dict(report='raw')),
+    ("nowarm", dict(warm_up_days=0)),
+    ("noextra", dict(extra=None)),
+    ("nowarm_noextra", dict(warm_up_days=0, extra=None)),
+    ("warm30_raw", dict(warm_up_days=30, report='raw')),
+])
+def test_single_run_matches_reference(catchment, tag, kw):
+    _torch()
+    g = load_golden("runs_single")
+    eng = make_engine(catchment, obs=False, **kw)
+    res = eng.run(g["p_test"][None, :], discharge=True, scores=False, gw=True)
+    q = res["discharge"][:, 0].cpu().numpy()
+    assert q.shape == g["q_" + tag].shape
+    assert relmax(q, g["q_" + tag]) < RTOL_Q
+    assert abs(float(res["gw"][0]) - float(g["gw_" + tag])) < 1e-10 * float(g["gw_" + tag])
+
+
+def test_printed_known_answers(catchment):
+    """The reference's own known-answer test compares '%.6e' strings
+    (tests/test_run_daily_to_hourly.py:135-143); examples/out/ExampleDaily/ExampleDaily.mod.flow
+    holds the full 3653-day series at the same precision."""
+    _torch()
+    g = load_golden("runs_single")
+    printed = load_golden("example_daily_printed")["mod_flow"]
+    eng = make_engine(catchment, obs=False)
+    q = eng.run(g["p_test"][None, :], discharge=True, scores=False)["discharge"][:, 0].cpu().numpy()
+    assert ['%e' % v for v in q] == ['%e' % v for v in printed]
+    # three of the 91 values spelled out in the reference test (first, and the last two)
+    assert '%.6e' % q[-2] == '%.6e' % 6.7547748371e-01
+    assert '%.6e' % q[-1] == '%.6e' % 8.3091723923e-01
+
+
+# ---------------------------------------------------------------- members: LHS sample, range corners, .lhs rows
+@pytest.mark.parametrize("flags", [0, 1, 2, 3])   # default, FORCE_GENERAL, NO_TMA, both
+def test_members_match_reference_and_oracle_scores(catchment, flags):
+    _torch()
+    from oracle import scores as oscores
+    g = load_golden("runs_members")
+    eng = make_engine(catchment, flags=flags)
+    res = eng.run(g["params"], discharge=True, scores=True, gw=True)
+    q = res["discharge"].cpu().numpy().T
+    assert relmax(q, g["q"]) < RTOL_Q
+    gw = res["gw"].cpu().numpy()
+    assert relmax(gw, g["gw"]) < 1e-9
+    sc = res["scores"].cpu().numpy()
+    sc_ref = oscores.score_members(g["q"], g["gw"], catchment.obs, 0.12667)
+    assert np.max(np.abs(sc[:, :7] - sc_ref[:, :7]) / np.maximum(1.0, np.abs(sc_ref[:, :7]))) < 1e-10
+    assert np.array_equal(sc[:, 7], sc_ref[:, 7])
+    # the reference's only artefact pinning the objective functions: the float32 .lhs file
+    n0 = int(g["n_lhs"]) + int(g["n_corners"])
+    file_scores = g["file_scores"].astype(np.float64)
+    assert np.max(np.abs(sc[n0:, :5] - file_scores[:, :5])) < 5e-7
+    assert np.max(np.abs(sc[n0:, 5:7] - file_scores[:, 5:7]) / np.abs(file_scores[:, 5:7])) < 5e-7
+    assert np.array_equal(sc[n0:, 7], file_scores[:, 7])
+
+
+def test_scores_only_equals_scores_with_discharge(catchment):
+    _torch()
+    g = load_golden("runs_members")
+    eng = make_engine(catchment, n_steps=24 * 400)
+    a = eng.run(g["params"], discharge=True, scores=True)
+    b = eng.run(g["params"], discharge=False, scores=True)
+    assert np.array_equal(a["scores"].cpu().numpy(), b["scores"].cpu().numpy(), equal_nan=True)
+
+
+def test_best_member(catchment):
+    _torch()
+    g = load_golden("runs_members")
+    eng = make_engine(catchment, n_steps=24 * 500)
+    res = eng.run(np.tile(g["params"], (8, 1)), scores=True, best=('KGE', 1))
+    sc = res["scores"].cpu().numpy()
+    score, index = res["best"]
+    assert int(index.item()) == int(np.argmax(sc[:, 1]))      # ties -> lowest index, like argmax
+    assert float(score.item()) == sc[:, 1].max()
+    res = eng.run(g["params"], scores=True, best=('RMSE', -1))
+    sc = res["scores"].cpu().numpy()
+    assert int(res["best"][1].item()) == int(np.argmin(sc[:, 6]))
+
+
+# ---------------------------------------------------------------- daily time step: clamps + 95 % river cap fire
+@pytest.mark.parametrize("tag,report,warm,gap", [
+    ("g1_summary_w365", "summary", 365, 1),
+    ("g13_summary_w0", "summary", 0, 13),
+    ("g13_raw_w365", "raw", 365, 13),
+    ("g13_summary_w26", "summary", 26, 13),
+])
+def test_daily_step_matches_reference(tag, report, warm, gap):
+    _torch()
+    from smartpy_b200.engine import BatchEngine
+    g = load_golden("runs_daily")
+    area = float(load_golden("catchment_processed")["area_m2"])
+    eng = BatchEngine(g["rain"], g["peva"], area, 86400.0, gap, extra=EXTRA, warm_up_steps=warm, report=report)
+    res = eng.run(g["params"], discharge=True, scores=False, gw=True)
+    q = res["discharge"].cpu().numpy().T
+    ref = g["q_" + tag]
+    assert q.shape == ref.shape
+    # a discharge that has decayed to ~1e-300 carries no relative information: floor the scale
+    scale = np.maximum(np.abs(ref), 1e-12 * np.abs(ref).max(axis=1, keepdims=True))
+    assert np.max(np.abs(q - ref) / scale) < RTOL_Q
+    assert relmax(res["gw"].cpu().numpy(), g["gw_" + tag]) < 1e-9
+
+
+def test_error_behaviour_matches_reference():
+    _torch()
+    from smartpy_b200.engine import BatchEngine
+    g = load_golden("runs_daily")
+    assert bool(g["summary_w365_g13_raises"])     # the reference raises ValueError (np.reshape)
+    eng = BatchEngine(g["rain"], g["peva"], 1e8, 86400.0, 13, extra=EXTRA, warm_up_steps=365, report='summary')
+    with pytest.raises(ValueError):
+        eng.run(g["params"][:2], discharge=True, scores=False)
+    eng = BatchEngine(g["rain"][:100], g["peva"][:100], 1e8, 86400.0, 1, warm_up_steps=101)
+    with pytest.raises(Exception, match="warm-up"):           # structure.py:90-95
+        eng.run(g["params"][:2], discharge=True, scores=False)
+    with pytest.raises(Exception, match="unknown"):           # structure.py:70
+        BatchEngine(g["rain"], g["peva"], 1e8, 86400.0, 1, report='mean')
+
+
+# ---------------------------------------------------------------- smartcpp.allsteps contract
+def test_allsteps_host_matches_reference():
+    _torch()
+    from smartpy_b200 import smartcpp_shim
+    g = load_golden("runs_single")
+    proc = load_golden("catchment_processed")
+    rain = np.repeat(proc["rain_hourly_per_day"], 24)
+    peva = np.repeat(proc["peva_hourly_per_day"], 24)
+    q, gw, last = smartcpp_shim.allsteps(float(proc["area_m2"]), 3600.0, 4800, rain, peva, g["p_test"],
+                                         g["allsteps_init"], 2, 1)
+    assert relmax(q, g["allsteps_q_hourly"]) < RTOL_Q
+    assert abs(gw - float(g["allsteps_gw"])) < 1e-10
+    assert relmax(last[7:], g["allsteps_last"][7:]) < RTOL_Q
+    one = load_golden("one_step")
+    for i in (0, 3, 5, 17, 34):     # in range, out of range (i % 5 == 0), exact wet/dry ties (i % 17 == 0)
+        out = np.asarray(smartcpp_shim.onestep(*one["cases"][i]))
+        ref = one["outs"][i]
+        scale = np.maximum(np.abs(ref), 1e-9 * np.abs(ref).max())
+        assert np.max(np.abs(out - ref) / scale) < 1e-9
+
+
+def test_one_step_known_answers_through_allsteps():
+    """400 reference run_one_step cases (in and out of the parameter ranges) as 1-step runs."""
+    _torch()
+    from smartpy_b200.engine import BatchEngine
+    g = load_golden("one_step")
+    worst = 0.0
+    for dt in (3600.0, 86400.0, 900.0):
+        sel = np.where(g["cases"][:, 1] == dt)[0]
+        for i in sel[:40]:
+            c, ref = g["cases"][i], g["outs"][i]
+            eng = BatchEngine(c[2:3], c[3:4], c[0], dt, 1, report='raw')
+            init = np.zeros((1, 19))
+            init[0, 7:] = c[14:]
+            res = eng.run(c[4:14][None, :], discharge=True, scores=False, gw=False, last_state=True,
+                          initial_state=init)
+            q = float(res["discharge"][0, 0])
+            last = res["last_state"][0].cpu().numpy()
+            scale = max(abs(ref[6]), 1e-9)
+            worst = max(worst, abs(q - ref[6]) / scale)
+            vs = np.maximum(np.abs(ref[7:]), 1e-6 * c[0] / 1e3)   # 1e-6 mm of water
+            worst = max(worst, float(np.max(np.abs(last[7:] - ref[7:]) / vs)))
+    assert worst < 1e-9
+
+
+# ---------------------------------------------------------------- multi-catchment batches ([t][catchment] forcing)
+@pytest.mark.parametrize("n_catch,mpc", [(6, 50), (3, 200), (10, 7)])
+def test_multi_catchment_matches_oracle(catchment, oracle_lib, n_catch, mpc):
+    _torch()
+    from smartpy_b200.engine import BatchEngine, warm_up_length
+    from oracle import scores as oscores
+    rng = np.random.RandomState(123)
+    n_steps = 24 * 120
+    rain = np.stack([catchment.rain[k * 500:k * 500 + n_steps] * rng.uniform(0.5, 1.5) for k in range(n_catch)], 1)
+    peva = np.stack([catchment.peva[k * 300:k * 300 + n_steps] * rng.uniform(0.8, 1.2) for k in range(n_catch)], 1)
+    area = 10 ** rng.uniform(7, 9, n_catch)
+    obs = np.stack([catchment.obs[k * 10:k * 10 + n_steps // 24] for k in range(n_catch)], 1)
+    base = load_golden("runs_members")["params"]
+    params = base[rng.randint(0, len(base), n_catch * mpc)]
+    eng = BatchEngine(rain, peva, area, 3600.0, 24, obs=obs, extra=EXTRA,
+                      warm_up_steps=warm_up_length(30, 3600.0), members_per_catchment=mpc)
+    res = eng.run(params, discharge=True, scores=True, gw=True)
+    q = res["discharge"].cpu().numpy().T
+    sc = res["scores"].cpu().numpy()
+    pick = rng.choice(n_catch * mpc, 24, replace=False)
+    for m in pick:
+        c = m // mpc
+        q_ref, gw_ref = oracle_lib.run(area[c], 3600.0, rain[:, c].copy(), peva[:, c].copy(), params[m], EXTRA,
+                                       n_steps, 24, warm_up=30)
+        assert relmax(q[m], q_ref) < RTOL_Q
+        s_ref = oscores.objectivefunction((q_ref, [gw_ref]), (obs[:, c], [None]))
+        assert np.max(np.abs(sc[m, :7] - np.array(s_ref)) / np.maximum(1.0, np.abs(s_ref))) < 1e-9
+        assert np.isnan(sc[m, 7])
+
+
+# ---------------------------------------------------------------- ragged sizes: odd lengths, partial chunks, tails
+@pytest.mark.parametrize("n_steps,gap,report,n_members", [
+    (1, 1, 'raw', 1), (511, 1, 'summary', 3), (513, 3, 'raw', 129), (1025, 5, 'summary', 257), (2000, 7, 'raw', 5)])
+def test_ragged_shapes_match_oracle(catchment, oracle_lib, n_steps, gap, report, n_members):
+    _torch()
+    from smartpy_b200.engine import BatchEngine
+    base = load_golden("runs_members")["params"]
+    params = np.resize(base, (n_members, 10))
+    rain, peva = catchment.rain[100:100 + n_steps].copy(), catchment.peva[100:100 + n_steps].copy()
+    warm = 0 if report == 'summary' and n_steps < gap else (n_steps // gap // 2) * gap
+    for flags in (0, 2):
+        eng = BatchEngine(rain, peva, catchment.area, 3600.0, gap, extra=EXTRA, warm_up_steps=warm, report=report,
+                          flags=flags)
+        res = eng.run(params, discharge=True, scores=False, gw=True)
+        q = res["discharge"].cpu().numpy().T
+        for m in (0, n_members - 1):
+            q_ref, gw_ref = oracle_lib.run(catchment.area, 3600.0, rain, peva, params[m], EXTRA, n_steps, gap,
+                                           report=report, warm_up=warm * 3600.0 / 86400.0)
+            assert q[m].shape == q_ref.shape
+            assert relmax(q[m], q_ref) < RTOL_Q
+
+
+# ---------------------------------------------------------------- FP32 mode
+def test_fp32_mode_scores_within_tolerance(catchment):
+    _torch()
+    from oracle import scores as oscores
+    g = load_golden("runs_members")
+    eng = make_engine(catchment, precision='f32')
+    res = eng.run(g["params"], discharge=True, scores=True, gw=True)
+    sc = res["scores"].cpu().numpy()
+    sc_ref = oscores.score_members(g["q"], g["gw"], catchment.obs, 0.12667)
+    assert np.max(np.abs(sc[:, 0] - sc_ref[:, 0])) < ATOL_F32     # NSE
+    assert np.max(np.abs(sc[:, 1] - sc_ref[:, 1])) < ATOL_F32     # KGE
+    assert res["discharge"].dtype == _torch().float32
+
+
+# ---------------------------------------------------------------- host-pointer entry point
+def test_batch_run_host_entry_point(catchment):
+    _torch()
+    from smartpy_b200 import _native
+    lib = _native.load()
+    g = load_golden("runs_members")
+    n, days = 5, 200
+    params = np.ascontiguousarray(g["params"][:n])
+    rain = np.ascontiguousarray(catchment.rain[:days * 24])
+    peva = np.ascontiguousarray(catchment.peva[:days * 24])
+    obs = np.ascontiguousarray(catchment.obs[:days])
+    area = np.array([catchment.area])
+    q = np.zeros((days, n))
+    sc = np.zeros((n, 8))
+    gw = np.zeros(n)
+    d = _native.BatchDesc()
+    d.n_members, d.n_steps, d.n_warmup, d.n_catchments, d.members_per_catchment = n, days * 24, 24 * 30, 1, 1
+    d.report_gap, d.report_type, d.dt_sec = 24, 1, 3600.0
+    d.params, d.rain, d.peva = params.ctypes.data, rain.ctypes.data, peva.ctypes.data
+    d.area_m2, d.obs = area.ctypes.data, obs.ctypes.data
+    d.has_extra, d.aar, d.ro_ratio = 1, 1200.0, 0.45
+    for k in range(5):
+        d.ro_split[k] = EXTRA['r-o_split'][k]
+    d.gw_constraint = float('nan')
+    d.discharge, d.ld_discharge, d.scores, d.gw = q.ctypes.data, n, sc.ctypes.data, gw.ctypes.data
+    _native.check(lib.smart_batch_run_host(ctypes.byref(d), 64, 0))
+    import oracle
+    q_ref, gw_ref = oracle.run_members(catchment.area, 3600.0, rain, peva, params, EXTRA, days * 24, 24, warm_up=30)
+    assert relmax(q.T, q_ref) < RTOL_Q
+    assert relmax(gw, gw_ref) < 1e-9
