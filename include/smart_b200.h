@@ -121,6 +121,15 @@ int smart_batch_run_f64(const smart_batch_desc *d, void *stream);
 int smart_batch_run_f32(const smart_batch_desc *d, void *stream);
 
 /*
+ * Objective functions of already simulated series (montecarlo.py:193-209 on its own):
+ * discharge[n_report][ld] (double when precision == 64, float when 32) against
+ * obs[n_report][C] -> scores[N][8] with the GW column left NaN.  Device pointers.
+ */
+int smart_score_discharge(const void *discharge, int64_t ld_discharge, int64_t n_members, int64_t n_report,
+                          const double *obs, const double *obs_stats, int32_t n_catchments,
+                          int32_t members_per_catchment, int precision, double *scores, void *stream);
+
+/*
  * Same, with HOST pointers everywhere in *d (workspace/obs_stats ignored: handled inside).
  * Allocates device buffers, copies in, runs, copies out, synchronises.  precision: 64 | 32.
  */

@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmart_b200.so")
+# SMART_B200_LIB lets kernel-tuning experiments load an alternative build of the same ABI
+LIB_PATH = os.environ.get("SMART_B200_LIB") or os.path.join(_HERE, "libsmart_b200.so")
 
 N_PARAMS = 10
 N_VARS = 19
@@ -30,7 +31,8 @@ FLAG_NO_TMA = 0x2
 # every symbol include/smart_b200.h declares
 SYMBOLS = (
     "smart_version", "smart_last_error", "smart_batch_n_report", "smart_batch_workspace_bytes",
-    "smart_obs_stats", "smart_batch_run_f64", "smart_batch_run_f32", "smart_batch_run_host",
+    "smart_obs_stats", "smart_batch_run_f64", "smart_batch_run_f32", "smart_score_discharge",
+    "smart_batch_run_host",
     "smart_allsteps_host", "smart_fma_peak_probe",
 )
 
@@ -107,6 +109,10 @@ def load():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
         fn.argtypes = [pdesc, ctypes.c_void_p]
+    lib.smart_score_discharge.restype = ctypes.c_int
+    lib.smart_score_discharge.argtypes = [
+        ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int32, ctypes.c_int32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
     lib.smart_batch_run_host.restype = ctypes.c_int
     lib.smart_batch_run_host.argtypes = [pdesc, ctypes.c_int, ctypes.c_int]
     lib.smart_allsteps_host.restype = ctypes.c_int

@@ -16,6 +16,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -24,10 +25,13 @@ namespace {
 
 using namespace smart;
 
-constexpr int kBlock = 128;        // members per CTA
 constexpr int kChunkSingle = 512;  // forcing steps per smem stage, single catchment
-constexpr int kAccSlots = 6;       // per-thread binary64 accumulators parked in smem
+constexpr int kAccSlots = 7;       // per-thread binary64 accumulators parked in smem
+constexpr int kConstSlots = 7;     // per-thread constants of the fast step parked in smem
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
+#ifndef SMART_FAST_REGS_F64
+#define SMART_FAST_REGS_F64 88     // register budget of the fast FP64 kernel: 23 warps per SM
+#endif
 
 thread_local std::string g_err;
 
@@ -104,88 +108,109 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (spins > (1u << 26)) __trap();
 }
 
+// ------------------------------------------------------------------ shared-memory layout of one CTA
+//   [0, 128)                       two mbarriers (TMA stages), padded
+//   double rain[2][chunk * kc]     forcing stages
+//   double peva[2][chunk * kc]
+//   double acc[kAccSlots][BLOCK]   per-thread binary64 accumulators touched once per report step
+//   R      kconst[kConstSlots][BLOCK]  per-thread constants of the fast step (see smart_step_fast)
+enum : int { kVariantFast = 0, kVariantGeneral = 1, kVariantFluxes = 2 };
+
+template <typename R, int BLOCK>
+struct Smem {
+    uint64_t *full;
+    double *rain, *peva, *acc;
+    R *kconst;
+    __device__ __forceinline__ Smem(unsigned char *raw, int tile)
+    {
+        full = reinterpret_cast<uint64_t *>(raw);
+        rain = reinterpret_cast<double *>(raw + kSmemHeader);
+        peva = rain + 2 * tile;
+        acc = peva + 2 * tile;
+        kconst = reinterpret_cast<R *>(acc + kAccSlots * BLOCK);
+    }
+};
+
 // ------------------------------------------------------------------ the time loop
-template <typename R, bool kGeneral, bool kFluxes>
+template <typename R, int kVariant, int BLOCK>
 __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
-                                             unsigned char *smem_raw, long long m, bool active, int c, int col,
+                                             const Smem<R, BLOCK> &sm, long long m, bool active, int c, int col,
                                              int c_base, double area, double &gw_out, StepOut<R> &o)
 {
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
+    constexpr bool kFast = kVariant == kVariantFast;
     const int tile = a.chunk * a.kc;
-    double *s_rain = reinterpret_cast<double *>(smem_raw + kSmemHeader);   // [2][tile]
-    double *s_peva = s_rain + 2 * tile;                                   // [2][tile]
-    double *s_acc = s_peva + 2 * tile;                                    // [kAccSlots][kBlock]
     const int tid = threadIdx.x;
-    double &A = s_acc[0 * kBlock + tid];      // sum (s - ebar)
-    double &B = s_acc[1 * kBlock + tid];      // sum (s - ebar)^2
-    double &Cc = s_acc[2 * kBlock + tid];     // sum (s - ebar)(e - ebar)
-    double &E = s_acc[3 * kBlock + tid];      // sum (s - e)^2
-    double &GN = s_acc[4 * kBlock + tid];     // sum (Q_sgw + Q_dgw)
-    double &GD = s_acc[5 * kBlock + tid];     // sum of the five pathway flows
+    double &A = sm.acc[0 * BLOCK + tid];      // sum (s - ebar)
+    double &B = sm.acc[1 * BLOCK + tid];      // sum (s - ebar)^2
+    double &Cc = sm.acc[2 * BLOCK + tid];     // sum (s - ebar)(e - ebar)
+    double &E = sm.acc[3 * BLOCK + tid];      // sum (s - e)^2
+    double &GN = sm.acc[4 * BLOCK + tid];     // sum (Q_sgw + Q_dgw)
+    double &GD = sm.acc[5 * BLOCK + tid];     // sum of the five pathway flows
+    double &RIV0 = sm.acc[6 * BLOCK + tid];   // river store at the start of the main run
+    const R *kconst = sm.kconst + tid;
 
     const int chunk = a.chunk, kc = a.kc;
-    const long long nWc = (a.W + chunk - 1) / chunk;
-    const long long nMc = (a.T + chunk - 1) / chunk;
-    const long long nTot = nWc + nMc;
+    const int nWc = static_cast<int>((a.W + chunk - 1) / chunk);
+    const int nTot = nWc + static_cast<int>((a.T + chunk - 1) / chunk);
     const bool summary = a.report_type == SMART_REPORT_SUMMARY;
-    const double ebar = a.obs ? a.obs_stats[c * SMART_OBS_STATS + 2] : 0.0;
-    const R qscale = static_cast<R>(area / (1e3 * a.dt));          // mm per step -> m3/s
-    const R mean_scale = static_cast<R>(area / (1e3 * a.dt) / static_cast<double>(a.gap));
 
-    auto chunk_span = [&](long long ci, long long &t0, int &n) {
+    auto chunk_span = [&](int ci, long long &t0, int &n) {
         if (ci < nWc) {
-            t0 = ci * chunk;
+            t0 = static_cast<long long>(ci) * chunk;
             n = static_cast<int>(min(static_cast<long long>(chunk), a.W - t0));
         } else {
-            t0 = (ci - nWc) * chunk;
+            t0 = static_cast<long long>(ci - nWc) * chunk;
             n = static_cast<int>(min(static_cast<long long>(chunk), a.T - t0));
         }
     };
     // TMA producer (one thread): even element counts go through cp.async.bulk (16-byte
     // granules); an odd tail element is placed with a plain store BEFORE the releasing arrive.
-    auto tma_issue = [&](long long ci) {
+    auto tma_issue = [&](int ci) {
         long long t0;
         int n;
         chunk_span(ci, t0, n);
-        const int b = static_cast<int>(ci & 1);
-        double *dr = s_rain + b * tile, *dp = s_peva + b * tile;
+        const int b = ci & 1;
+        double *dr = sm.rain + b * tile, *dp = sm.peva + b * tile;
         const int n_even = n & ~1;
         if (n & 1) {
             dr[n - 1] = a.rain[t0 + n - 1];
             dp[n - 1] = a.peva[t0 + n - 1];
         }
-        mbar_arrive_expect_tx(&full[b], 2u * n_even * 8u);
+        mbar_arrive_expect_tx(&sm.full[b], 2u * n_even * 8u);
         if (n_even) {
-            tma_bulk_g2s(dr, a.rain + t0, n_even * 8u, &full[b]);
-            tma_bulk_g2s(dp, a.peva + t0, n_even * 8u, &full[b]);
+            tma_bulk_g2s(dr, a.rain + t0, n_even * 8u, &sm.full[b]);
+            tma_bulk_g2s(dp, a.peva + t0, n_even * 8u, &sm.full[b]);
         }
     };
 
     int countdown = 0x7fffffff;   // never fires during the warm-up
-    long long r = 0;
+    int r = 0;
     R acc = R(0), agw = R(0), aall = R(0);
+    FastCarry<R> carry;
+    carry.tot = R(0);
+    carry.valid = false;
     o.q_riv = o.q_gw = o.q_all = R(0);
     o.aeva = o.q_ove = o.q_dra = o.q_int = o.q_sgw = o.q_dgw = R(0);
 
     if (a.use_tma && tid == 0) tma_issue(0);
 
-    for (long long ci = 0; ci < nTot; ++ci) {
-        const int b = static_cast<int>(ci & 1);
+    for (int ci = 0; ci < nTot; ++ci) {
+        const int b = ci & 1;
         long long t0;
         int n;
         chunk_span(ci, t0, n);
         if (a.use_tma) {
             if (tid == 0 && ci + 1 < nTot) tma_issue(ci + 1);
-            mbar_wait(&full[b], static_cast<uint32_t>((ci >> 1) & 1));
+            mbar_wait(&sm.full[b], static_cast<uint32_t>((ci >> 1) & 1));
         } else {
             // coalesced tile load: rows t0..t0+n, columns c_base..c_base+kc of [T][C]
-            for (int idx = tid; idx < n * kc; idx += kBlock) {
+            for (int idx = tid; idx < n * kc; idx += BLOCK) {
                 const int row = idx / kc, cc = idx - row * kc;
                 const int cg = c_base + cc;
                 const bool ok = cg < a.C;
                 const long long g = (t0 + row) * static_cast<long long>(a.C) + cg;
-                s_rain[b * tile + idx] = ok ? a.rain[g] : 0.0;
-                s_peva[b * tile + idx] = ok ? a.peva[g] : 0.0;
+                sm.rain[b * tile + idx] = ok ? a.rain[g] : 0.0;
+                sm.peva[b * tile + idx] = ok ? a.peva[g] : 0.0;
             }
             __syncthreads();
         }
@@ -194,31 +219,41 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
             r = 0;
             acc = agw = aall = R(0);
             A = B = Cc = E = GN = GD = 0.0;
+            RIV0 = static_cast<double>(s.riv);
         }
-        const double *fr = s_rain + b * tile + col;
-        const double *fp = s_peva + b * tile + col;
+        const double *fr = sm.rain + b * tile + col;
+        const double *fp = sm.peva + b * tile + col;
         for (int i = 0; i < n; ++i) {
-            smart_step<R, kGeneral, kFluxes>(s, p, fr[i * kc], fp[i * kc], o);
+            if (kFast) {
+                smart_step_fast<R, BLOCK>(s, p, kconst, carry, fr[i * kc], fp[i * kc], o);
+            } else {
+                smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[i * kc], fp[i * kc], o);
+                aall += o.q_all;
+            }
             acc += o.q_riv;
             agw += o.q_gw;
-            aall += o.q_all;
             if (--countdown == 0) {
                 countdown = a.gap;
                 R sval;
                 if (summary) {
-                    sval = acc * mean_scale;                 // structure.py:190
+                    sval = acc * static_cast<R>(area / (1e3 * a.dt) / static_cast<double>(a.gap));   // structure.py:190
+                    // fast form: the pathway total is recovered from the river's mass balance at the
+                    // end (sum q_in = sum q_out + dV_river), so only sum q_out is accumulated here
+                    if (kFast) aall = acc;
                 } else {
-                    sval = o.q_riv * qscale;                 // structure.py:193
+                    sval = o.q_riv * static_cast<R>(area / (1e3 * a.dt));                           // structure.py:193
                     agw = o.q_gw;                            // :194-195 sample the same rows
                     aall = o.q_all;
                 }
                 GN += static_cast<double>(agw);
                 GD += static_cast<double>(aall);
                 acc = agw = aall = R(0);
-                if (a.discharge != nullptr && active) static_cast<R *>(a.discharge)[r * a.ld_q + m] = sval;
+                if (a.discharge != nullptr && active)
+                    static_cast<R *>(a.discharge)[static_cast<long long>(r) * a.ld_q + m] = sval;
                 if (a.obs != nullptr) {
-                    const double e = __ldg(&a.obs[r * a.C + c]);
+                    const double e = __ldg(&a.obs[static_cast<long long>(r) * a.C + c]);
                     if (e == e) {                            // montecarlo.py:195-196 NaN mask
+                        const double ebar = a.obs_stats[c * SMART_OBS_STATS + 2];
                         const double ds = static_cast<double>(sval) - ebar;
                         const double de = e - ebar;
                         const double df = ds - de;
@@ -233,13 +268,37 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         }
         __syncthreads();   // every thread is done with stage b before it is refilled
     }
-    gw_out = GN / GD;
+    double gd = GD;
+    if (kFast && summary) gd += static_cast<double>(s.riv) - RIV0;
+    gw_out = GN / gd;
 }
 
-template <typename R, bool kGeneral, bool kFluxes>
+// Final objective functions from the shifted sums (montecarlo.py:199-203; formulas of
+// spotpy.objectivefunctions nashsutcliffe / kge / pbias / rmse restated in DESIGN.md).
+__device__ __forceinline__ void finish_scores(const double *st, double A, double B, double Cc, double E,
+                                              double *sc)
+{
+    const double n = st[0], sum_e = st[1], ebar = st[2], sde = st[3], sse = st[4];
+    const double var_s = B - A * A / n;           // n * variance of the simulation
+    const double var_e = sse - sde * sde / n;     // n * variance of the observations
+    const double cov = Cc - A * sde / n;
+    sc[0] = 1.0 - E / sse;                                    // NSE
+    sc[2] = cov / sqrt(var_s * var_e);                        // KGEc (Pearson r)
+    sc[3] = sqrt(var_s / var_e);                              // KGEa
+    sc[4] = (A + n * ebar) / sum_e;                           // KGEb
+    sc[1] = 1.0 - sqrt((sc[2] - 1.0) * (sc[2] - 1.0) + (sc[3] - 1.0) * (sc[3] - 1.0) +
+                       (sc[4] - 1.0) * (sc[4] - 1.0));        // KGE
+    sc[5] = 100.0 * ((A - sde) / sum_e);                      // PBias
+    sc[6] = sqrt(E / n);                                      // RMSE
+}
+
+template <typename R, int kVariant, int BLOCK>
 __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
                                            long long m, bool active, int c, int col, int c_base, double area)
 {
+    constexpr bool kFast = kVariant == kVariantFast;
+    const int tid = threadIdx.x;
+    const Smem<R, BLOCK> sm(smem_raw, a.chunk * a.kc);
     const double T = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
     const double SK = par[6], FK = par[7], GK = par[8], RK = par[9];
     MemberPar<R> p;
@@ -250,10 +309,22 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
     p.Hz = static_cast<R>(H / Z);
     p.Sz = static_cast<R>(S / Z);
     p.z = static_cast<R>(Z / 6.0);
-    p.r_sk = static_cast<R>(a.dt / (SK * 3600.0));
-    p.r_fk = static_cast<R>(a.dt / (FK * 3600.0));
-    p.r_gk = static_cast<R>(a.dt / (GK * 3600.0));
-    p.r_rk = static_cast<R>(a.dt / (RK * 3600.0));
+    const double r_sk = a.dt / (SK * 3600.0), r_fk = a.dt / (FK * 3600.0);
+    const double r_gk = a.dt / (GK * 3600.0), r_rk = a.dt / (RK * 3600.0);
+    p.r_sk = static_cast<R>(r_sk);
+    p.r_fk = static_cast<R>(r_fk);
+    p.r_gk = static_cast<R>(r_gk);
+    p.r_rk = static_cast<R>(r_rk);
+    if (kFast) {
+        R *kconst = sm.kconst + tid;
+        kconst[0 * BLOCK] = p.C;
+        kconst[1 * BLOCK] = p.D;
+        kconst[2 * BLOCK] = p.omD;
+        kconst[3 * BLOCK] = static_cast<R>(1.0 - r_sk);
+        kconst[4 * BLOCK] = static_cast<R>(1.0 - r_fk);
+        kconst[5 * BLOCK] = static_cast<R>(1.0 - r_gk);
+        kconst[6 * BLOCK] = static_cast<R>(1.0 - r_rk);
+    }
 
     // initial conditions in m3 exactly as the reference writes them, then to mm
     const double to_mm = 1e3 / area;
@@ -279,7 +350,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 #pragma unroll
     for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(v[5 + k] * to_mm);
     s.riv = static_cast<R>(v[11] * to_mm);
-    if (!kGeneral) {   // same routing constant => one linear reservoir
+    if (kFast) {   // same routing constant => one linear reservoir
         s.ove = s.ove + s.dra;
         s.sgw = s.sgw + s.dgw;
         s.dra = s.dgw = R(0);
@@ -287,29 +358,15 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 
     double gw = 0.0;
     StepOut<R> o;
-    run_timeline<R, kGeneral, kFluxes>(a, s, p, smem_raw, m, active, c, col, c_base, area, gw, o);
+    run_timeline<R, kVariant, BLOCK>(a, s, p, sm, m, active, c, col, c_base, area, gw, o);
 
     // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
-    double *s_acc = reinterpret_cast<double *>(smem_raw + kSmemHeader) + 4 * a.chunk * a.kc;
-    const int tid = threadIdx.x;
     double target = -CUDART_INF;
     if (a.obs != nullptr) {
         const double *st = a.obs_stats + c * SMART_OBS_STATS;
-        const double n = st[0], sum_e = st[1], ebar = st[2], sde = st[3], sse = st[4];
-        const double A = s_acc[0 * kBlock + tid], B = s_acc[1 * kBlock + tid];
-        const double Cc = s_acc[2 * kBlock + tid], E = s_acc[3 * kBlock + tid];
-        const double var_s = B - A * A / n;           // n * variance of the simulation
-        const double var_e = sse - sde * sde / n;     // n * variance of the observations
-        const double cov = Cc - A * sde / n;
         double sc[SMART_N_SCORES];
-        sc[0] = 1.0 - E / sse;                                    // NSE
-        sc[2] = cov / sqrt(var_s * var_e);                        // KGEc (Pearson r)
-        sc[3] = sqrt(var_s / var_e);                              // KGEa
-        sc[4] = (A + n * ebar) / sum_e;                           // KGEb
-        sc[1] = 1.0 - sqrt((sc[2] - 1.0) * (sc[2] - 1.0) + (sc[3] - 1.0) * (sc[3] - 1.0) +
-                           (sc[4] - 1.0) * (sc[4] - 1.0));        // KGE
-        sc[5] = 100.0 * ((A - sde) / sum_e);                      // PBias
-        sc[6] = sqrt(E / n);                                      // RMSE
+        finish_scores(st, sm.acc[0 * BLOCK + tid], sm.acc[1 * BLOCK + tid], sm.acc[2 * BLOCK + tid],
+                      sm.acc[3 * BLOCK + tid], sc);
         const bool gw_on = a.gw_constraint == a.gw_constraint && a.gw_constraint != 0.0;
         sc[7] = gw_on ? ((a.gw_constraint - 0.1 <= gw && gw <= a.gw_constraint + 0.1) ? 1.0 : 0.0)
                       : CUDART_NAN;                               // objfunctions.py:20-24
@@ -326,7 +383,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         }
     }
     if (a.gw != nullptr && active) a.gw[m] = gw;
-    if (kFluxes && a.last_state != nullptr && active) {
+    if (kVariant == kVariantFluxes && a.last_state != nullptr && active) {
         // the 7 fluxes of the last step in m3/s, the 12 states back in m3 (structure.py:259-264)
         double *ls = a.last_state + m * SMART_N_VARS;
         const double to_m3 = area / 1e3;
@@ -359,16 +416,17 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
                 idx = oi;
             }
         }
-        __syncthreads();   // s_acc is free to reuse now
-        long long *s_idx = reinterpret_cast<long long *>(s_acc + kBlock);
+        __syncthreads();   // the accumulator slots are free to reuse now
+        double *s_t = sm.acc;
+        long long *s_idx = reinterpret_cast<long long *>(sm.acc + BLOCK);
         if ((tid & 31) == 0) {
-            s_acc[tid >> 5] = target;
+            s_t[tid >> 5] = target;
             s_idx[tid >> 5] = idx;
         }
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < kBlock / 32; ++w) {
-                const double ot = s_acc[w];
+            for (int w = 1; w < BLOCK / 32; ++w) {
+                const double ot = s_t[w];
                 const long long oi = s_idx[w];
                 if (ot > target || (ot == target && oi < idx)) {
                     target = ot;
@@ -381,18 +439,40 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
     }
 }
 
-template <typename R>
-__global__ void __launch_bounds__(kBlock) smart_batch_kernel(const KArgs a)
+// Variant of the step a kernel instantiation carries.  The choice depends on the members'
+// parameters, which live on the device, so the host launches the fast kernel and the general
+// kernel back to back on the same stream: every CTA votes (one __syncthreads_or) on whether
+// all of its members qualify for the merged form and runs in exactly one of the two launches;
+// in the other it exits at once.  Separate kernels keep the fast variant's register count
+// (and so its occupancy) independent of the branch-faithful code.
+template <typename R, int kVariant, int BLOCK, int MIN_BLOCKS>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) smart_batch_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const long long m_raw = static_cast<long long>(blockIdx.x) * kBlock + tid;
+    const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + tid;
     const bool active = m_raw < a.N;
     const long long m = active ? m_raw : a.N - 1;   // tail threads shadow the last member, store nothing
 
+    double par[SMART_N_PARAMS];
+#pragma unroll
+    for (int k = 0; k < SMART_N_PARAMS; ++k) par[k] = a.params[m * SMART_N_PARAMS + k];
+
+    if (kVariant != kVariantFluxes) {
+        // The merged form is exact only when no clamp, cap or leak predicate can fire:
+        // every routing constant >= dt, inflows >= 0 (0 <= D <= 1, 0 <= H < 1), s' < 1.
+        const double dt = a.dt;
+        bool fast_ok = par[6] * 3600.0 >= dt && par[7] * 3600.0 >= dt && par[8] * 3600.0 >= dt &&
+                       par[9] * 3600.0 >= dt && par[4] >= 0.0 && par[4] <= 0.5 && par[5] > 0.0 &&
+                       par[3] >= 0.0 && par[3] <= 1.0 && par[2] >= 0.0 && par[2] <= 0.99 && par[0] > 0.0;
+        fast_ok = fast_ok && !a.force_general && a.initial_state == nullptr;
+        const int need_general = __syncthreads_or(fast_ok ? 0 : 1);
+        if ((need_general != 0) != (kVariant == kVariantGeneral)) return;   // the other launch owns this CTA
+    }
+
     const bool multi = a.C > 1;
     const int c = multi ? static_cast<int>(m / a.mpc) : 0;
-    const int c_base = multi ? static_cast<int>((static_cast<long long>(blockIdx.x) * kBlock) / a.mpc) : 0;
+    const int c_base = multi ? static_cast<int>((static_cast<long long>(blockIdx.x) * BLOCK) / a.mpc) : 0;
     const int col = c - c_base;
     const double area = a.area[c];
 
@@ -403,27 +483,10 @@ __global__ void __launch_bounds__(kBlock) smart_batch_kernel(const KArgs a)
             mbar_init(&full[1], 1);
             mbar_fence_init();
         }
+        __syncthreads();
     }
 
-    double par[SMART_N_PARAMS];
-#pragma unroll
-    for (int k = 0; k < SMART_N_PARAMS; ++k) par[k] = a.params[m * SMART_N_PARAMS + k];
-
-    // The merged form is exact only when no clamp, cap or leak predicate can fire:
-    // every routing constant >= dt, inflows >= 0 (0 <= D <= 1, 0 <= H < 1), s' < 1.
-    const double dt = a.dt;
-    bool fast_ok = par[6] * 3600.0 >= dt && par[7] * 3600.0 >= dt && par[8] * 3600.0 >= dt &&
-                   par[9] * 3600.0 >= dt && par[4] >= 0.0 && par[4] <= 0.5 && par[5] > 0.0 &&
-                   par[3] >= 0.0 && par[3] <= 1.0 && par[2] >= 0.0 && par[2] <= 0.99 && par[0] >= 0.0;
-    fast_ok = fast_ok && !a.force_general && a.last_state == nullptr && a.initial_state == nullptr;
-    const int need_general = __syncthreads_or(fast_ok ? 0 : 1);   // also orders the mbarrier init
-
-    if (a.last_state != nullptr)
-        run_member<R, true, true>(a, smem_raw, par, m, active, c, col, c_base, area);
-    else if (need_general)
-        run_member<R, true, false>(a, smem_raw, par, m, active, c, col, c_base, area);
-    else
-        run_member<R, false, false>(a, smem_raw, par, m, active, c, col, c_base, area);
+    run_member<R, kVariant, BLOCK>(a, smem_raw, par, m, active, c, col, c_base, area);
 }
 
 __global__ void best_finalize_kernel(const double *blk_score, const long long *blk_index, int n_blocks, int sign,
@@ -511,6 +574,35 @@ __global__ void obs_stats_kernel(const double *obs, long long n_report, int C, d
     }
 }
 
+template <typename R>
+__global__ void score_discharge_kernel(const R *q, long long ld, long long N, long long n_report, const double *obs,
+                                       const double *obs_stats, int C, int mpc, double *scores)
+{
+    const long long m = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (m >= N) return;
+    const int c = C > 1 ? static_cast<int>(m / mpc) : 0;
+    const double *st = obs_stats + c * SMART_OBS_STATS;
+    const double ebar = st[2];
+    double A = 0.0, B = 0.0, Cc = 0.0, E = 0.0;
+    for (long long r = 0; r < n_report; ++r) {
+        const double e = __ldg(&obs[r * C + c]);
+        if (e == e) {
+            const double ds = static_cast<double>(q[r * ld + m]) - ebar;
+            const double de = e - ebar;
+            const double df = ds - de;
+            A += ds;
+            B = fma(ds, ds, B);
+            Cc = fma(ds, de, Cc);
+            E = fma(df, df, E);
+        }
+    }
+    double sc[SMART_N_SCORES];
+    finish_scores(st, A, B, Cc, E, sc);
+    sc[7] = CUDART_NAN;
+#pragma unroll
+    for (int k = 0; k < SMART_N_SCORES; ++k) scores[m * SMART_N_SCORES + k] = sc[k];
+}
+
 template <typename R, int kChains>
 __global__ void fma_peak_kernel(long long iters, double *out)
 {
@@ -536,14 +628,30 @@ int64_t n_report_of(const smart_batch_desc *d)
                                                   : (d->n_steps + d->report_gap - 1) / d->report_gap;
 }
 
-int n_blocks_of(const smart_batch_desc *d) { return static_cast<int>((d->n_members + kBlock - 1) / kBlock); }
+constexpr int kBlockSmall = 64, kBlockLarge = 128;
+
+// Members per CTA.  Members cost the same, so a launch finishes when the SM with the most
+// members does: 64-thread CTAs spread a batch of a few waves more evenly over the 148 SMs
+// (config C2: 1e5 members = 675.7 per SM); 128-thread CTAs halve the per-CTA staging for
+// batches of many waves.  SMART_B200_BLOCK overrides the choice (kernel tuning).
+int block_of(const smart_batch_desc *d)
+{
+    static const int forced = [] {
+        const char *e = getenv("SMART_B200_BLOCK");
+        return e ? atoi(e) : 0;
+    }();
+    if (forced == kBlockSmall || forced == kBlockLarge) return forced;
+    return d->n_members <= 148LL * 736 * 8 ? kBlockSmall : kBlockLarge;
+}
+
+int n_blocks_of(const smart_batch_desc *d, int block) { return static_cast<int>((d->n_members + block - 1) / block); }
 
 int validate(const smart_batch_desc *d, bool host_mode = false)
 {
     if (!d) return fail(SMART_ERR_BAD_ARG, "descriptor is NULL");
     if (d->n_members < 1 || d->n_steps < 1 || d->n_steps >= 0x7fffffffLL || d->n_warmup < 0)
         return fail(SMART_ERR_BAD_ARG, "n_members, n_steps must be >= 1 (n_steps < 2^31), n_warmup >= 0");
-    if (d->n_members > 0x7fffffffLL * kBlock) return fail(SMART_ERR_BAD_ARG, "n_members too large for one launch");
+    if (d->n_members > 0x7fffffffLL * kBlockSmall) return fail(SMART_ERR_BAD_ARG, "n_members too large for one launch");
     if (d->n_catchments < 1) return fail(SMART_ERR_BAD_ARG, "n_catchments must be >= 1");
     if (d->n_catchments > 1 &&
         (d->members_per_catchment < 1 ||
@@ -614,17 +722,18 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     const int64_t n_rep = n_report_of(d);
     a.first_report = static_cast<int>(d->n_steps - (n_rep - 1) * d->report_gap);
 
-    const int blocks = n_blocks_of(d);
+    const int block = block_of(d);
+    const int blocks = n_blocks_of(d, block);
     if (a.C == 1) {
         a.kc = 1;
-        a.chunk = kChunkSingle;
+        a.chunk = block == kBlockLarge ? kChunkSingle : kChunkSingle / 2;
         const bool aligned = (reinterpret_cast<uintptr_t>(d->rain) % 16 == 0) &&
                              (reinterpret_cast<uintptr_t>(d->peva) % 16 == 0);
         a.use_tma = (aligned && !(d->flags & SMART_FLAG_NO_TMA)) ? 1 : 0;
     } else {
-        a.kc = (kBlock - 1) / a.mpc + 2;              // catchments one CTA can straddle
+        a.kc = (block - 1) / a.mpc + 2;              // catchments one CTA can straddle
         if (a.kc > a.C) a.kc = a.C;
-        int chunk = (24 * 1024) / (2 * 2 * 8 * a.kc);
+        int chunk = (block == kBlockLarge ? 24 * 1024 : 12 * 1024) / (2 * 2 * 8 * a.kc);
         chunk = chunk > 512 ? 512 : chunk;
         chunk &= ~7;
         if (chunk < 8) return fail(SMART_ERR_BAD_ARG, "members_per_catchment too small for one CTA tile");
@@ -635,9 +744,33 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.blk_best_score = static_cast<double *>(d->workspace);
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
-    const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(a.chunk) * a.kc + kAccSlots * kBlock);
-    smart_batch_kernel<R><<<blocks, kBlock, smem, stream>>>(a);
-    SMART_CUDA(cudaGetLastError());
+    const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(a.chunk) * a.kc + kAccSlots * block) +
+                        sizeof(R) * kConstSlots * block;
+    // fast kernel: register budget -> resident CTAs per SM (FP64: 88 regs = 23 warps; FP32: 64 regs = 32 warps)
+    constexpr int kFastWarps = sizeof(R) == 8 ? 65536 / (SMART_FAST_REGS_F64 * 32) : 32;
+    const int variant = d->last_state ? kVariantFluxes : -1;
+    auto go = [&](auto kernel) -> int {
+        kernel<<<blocks, block, smem, stream>>>(a);
+        SMART_CUDA(cudaGetLastError());
+        return SMART_OK;
+    };
+    if (block == kBlockLarge) {
+        if (variant == kVariantFluxes) {
+            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockLarge, 1>))) return rc;
+        } else {
+            if (!a.force_general && !d->initial_state)
+                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockLarge, kFastWarps / 4>))) return rc;
+            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockLarge, 1>))) return rc;
+        }
+    } else {
+        if (variant == kVariantFluxes) {
+            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockSmall, 1>))) return rc;
+        } else {
+            if (!a.force_general && !d->initial_state)
+                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockSmall, kFastWarps / 2>))) return rc;
+            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockSmall, 1>))) return rc;
+        }
+    }
     if (d->best_sign != 0) {
         best_finalize_kernel<<<1, 32, 0, stream>>>(a.blk_best_score, a.blk_best_index, blocks, d->best_sign,
                                                    d->best_score, reinterpret_cast<long long *>(d->best_index));
@@ -668,7 +801,7 @@ int64_t smart_batch_n_report(const smart_batch_desc *d) { return d ? n_report_of
 size_t smart_batch_workspace_bytes(const smart_batch_desc *d)
 {
     if (!d || d->best_sign == 0) return 0;
-    return static_cast<size_t>(n_blocks_of(d)) * (sizeof(double) + sizeof(long long));
+    return static_cast<size_t>(n_blocks_of(d, kBlockSmall)) * (sizeof(double) + sizeof(long long));
 }
 
 int smart_obs_stats(const double *obs, int64_t n_report, int32_t n_catchments, double *stats, void *stream)
@@ -688,6 +821,31 @@ int smart_batch_run_f64(const smart_batch_desc *d, void *stream)
 int smart_batch_run_f32(const smart_batch_desc *d, void *stream)
 {
     return launch<float>(d, static_cast<cudaStream_t>(stream));
+}
+
+int smart_score_discharge(const void *discharge, int64_t ld_discharge, int64_t n_members, int64_t n_report,
+                          const double *obs, const double *obs_stats, int32_t n_catchments,
+                          int32_t members_per_catchment, int precision, double *scores, void *stream)
+{
+    if (!discharge || !obs || !obs_stats || !scores || n_members < 1 || n_report < 1 || n_catchments < 1 ||
+        ld_discharge < n_members || (n_catchments > 1 && members_per_catchment < 1))
+        return fail(SMART_ERR_BAD_ARG, "smart_score_discharge: bad argument");
+    const int threads = 128;
+    const int blocks = static_cast<int>((n_members + threads - 1) / threads);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int mpc = n_catchments > 1 ? members_per_catchment : 1;
+    if (precision == 64)
+        score_discharge_kernel<double><<<blocks, threads, 0, st>>>(static_cast<const double *>(discharge), ld_discharge,
+                                                                   n_members, n_report, obs, obs_stats, n_catchments,
+                                                                   mpc, scores);
+    else if (precision == 32)
+        score_discharge_kernel<float><<<blocks, threads, 0, st>>>(static_cast<const float *>(discharge), ld_discharge,
+                                                                  n_members, n_report, obs, obs_stats, n_catchments,
+                                                                  mpc, scores);
+    else
+        return fail(SMART_ERR_BAD_ARG, "precision must be 64 or 32");
+    SMART_CUDA(cudaGetLastError());
+    return SMART_OK;
 }
 
 int smart_batch_run_host(const smart_batch_desc *h, int precision, int device)

@@ -12,7 +12,9 @@
 // (:353-359) -- is evaluated exactly as the reference does: a rounded binary64 multiply, then
 // a rounded subtract (no FMA contraction), in binary64 even in FP32 mode.
 #pragma once
+#ifndef SMART_HOST_EMULATION   // tools/host_emulate.cpp compiles this header with g++ to study rounding
 #include <cuda_runtime.h>
+#endif
 
 namespace smart {
 
@@ -189,6 +191,139 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
         s.riv = (s.riv - q) + q_in;
         o.q_riv = q;
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// The merged ("fast") step: same model, fewer FP64-pipe instructions.  Valid under the same
+// conditions as kGeneral = false above (decided per CTA from the parameters).  Differences of
+// form with respect to smart_step<R, false>:
+//   * the soil total is only formed on wet steps (the dry branch never reads it) and is carried
+//     over from the end of the previous wet step when no dry step intervened (it is the same
+//     left-to-right sum of the same six values, so the carried number is bit-identical);
+//   * fill ladder in two additions per layer: w = level + excess, t = z - w; the layer takes
+//     everything iff t >= 0, else it is full and -t flows on (structure.py:367-374);
+//   * `x >= 0` tests on freshly computed differences read the sign bit (integer pipe) instead
+//     of issuing an FP64 compare; the wet/dry predicate itself stays an exact FP64 compare;
+//   * binary64 only: the three leak passes (structure.py:381-399) update each layer with one
+//     FMA per pass and obtain the interflow and groundwater inflows as differences of the soil
+//     total before/after (mass conserving by construction; absolute error of a few ulp of the
+//     soil total, i.e. ~1e-14 mm per wet step);
+//   * reservoirs advance with one FMA: V' = V * (1 - dt/k) + inflow, Q = V * (dt/k).
+// kc[] holds the per-member constants that are parked in shared memory:
+//   kc[0] = C, kc[1] = D, kc[2] = 1 - D, kc[3..6] = 1 - dt/k for SK, FK, GK, RK.
+template <typename R>
+struct FastCarry {
+    R tot;          // soil total at the end of the previous step, valid iff that step was wet
+    bool valid;
+};
+
+__device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
+__device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >= 0; }
+
+template <typename R, int kStride>
+__device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const MemberPar<R> &p, const R *kc,
+                                                FastCarry<R> &carry, double rain, double peva, StepOut<R> &o)
+{
+    constexpr bool kLeakByDifference = sizeof(R) == 8;
+    const R zero = R(0);
+    const double rain_c = __dmul_rn(rain, p.Td);        // structure.py:353-359, exact
+    const double ex_d = __dsub_rn(rain_c, peva);
+    R in_quick = zero, in_int = zero, in_gw = zero;
+
+    if (ex_d >= 0.0) {
+        R tot = carry.tot;
+        if (!carry.valid) tot = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+        const R ex = static_cast<R>(ex_d);
+        in_quick = (p.Hz * tot) * ex;                   // :363-364
+        const R u0 = in_quick - ex;                     // u = -(excess rain still to place) <= 0
+        R u = u0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {                   // :367-374
+            const R w = s.ly[i] - u;                    // level if the layer took everything
+            const R t = p.z - w;
+            const bool fits = sign_clear(t);
+            s.ly[i] = fits ? w : p.z;
+            u = fits ? zero : t;
+        }
+        in_quick = fma(kc[1 * kStride], -u, in_quick);  // + D * saturation excess (:376)
+        in_int = kc[2 * kStride] * (-u);                // (1 - D) * saturation excess (:377)
+        const R sp = p.Sz * tot;                        // :379
+        R pw[6];
+        pw[0] = sp;
+        pw[1] = sp * sp;
+        pw[2] = pw[1] * sp;
+        pw[3] = pw[1] * pw[1];
+        pw[4] = pw[3] * sp;
+        pw[5] = pw[2] * pw[2];
+        if (kLeakByDifference) {
+            // soil total after the fill, summed like tot1/tot3 so that a zero leak gives exactly 0
+            const R tot_f = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) s.ly[i] = fma(-s.ly[i], pw[i], s.ly[i]);            // :381-385
+            const R tot1 = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+            in_int += tot_f - tot1;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {                                                   // :388-399
+                const R f2 = i == 0 ? sp : sp * inv_const<R>(i);
+                s.ly[i] = fma(-s.ly[i], f2, s.ly[i]);
+            }
+#pragma unroll
+            for (int i = 5; i >= 0; --i) s.ly[i] = fma(-s.ly[i], pw[5 - i], s.ly[i]);
+            const R tot3 = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+            in_gw = tot1 - tot3;
+            carry.tot = tot3;
+            carry.valid = true;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const R leak = s.ly[i] * pw[i];
+                in_int += leak;
+                s.ly[i] -= leak;
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const R leak = s.ly[i] * (i == 0 ? sp : sp * inv_const<R>(i));
+                in_gw += leak;
+                s.ly[i] -= leak;
+            }
+#pragma unroll
+            for (int i = 5; i >= 0; --i) {
+                const R leak = s.ly[i] * pw[5 - i];
+                in_gw += leak;
+                s.ly[i] -= leak;
+            }
+            carry.valid = false;
+        }
+    } else {
+        R d = static_cast<R>(-ex_d);                    // :407-419
+        const R C = kc[0];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const R t = s.ly[i] - d;
+            const bool enough = sign_clear(t);          // level >= deficit
+            s.ly[i] = enough ? t : zero;
+            d = enough ? zero : C * (-t);
+        }
+        carry.valid = false;
+    }
+
+    // :427-450 with the SK/SK and GK/GK stores merged; :487-498 without the cap (cannot fire).
+    // binary64 advances a store with one FMA, V' = V * (1 - dt/k) + inflow; in binary32 the
+    // rounding of (1 - dt/k) would bias the recession constant by up to 1e-4, so the two-step
+    // form V' = (V - Q) + inflow is kept there.
+    constexpr bool kOneFma = sizeof(R) == 8;
+    const R q_quick = s.ove * p.r_sk;
+    s.ove = kOneFma ? fma(s.ove, kc[3 * kStride], in_quick) : (s.ove - q_quick) + in_quick;
+    const R q_int = s.itf * p.r_fk;
+    s.itf = kOneFma ? fma(s.itf, kc[4 * kStride], in_int) : (s.itf - q_int) + in_int;
+    const R q_gw = s.sgw * p.r_gk;
+    s.sgw = kOneFma ? fma(s.sgw, kc[5 * kStride], in_gw) : (s.sgw - q_gw) + in_gw;
+    o.q_gw = q_gw;
+    const R q_in = (q_quick + q_int) + q_gw;            // :254
+    o.q_all = q_in;
+    const R q = s.riv * p.r_rk;
+    s.riv = kOneFma ? fma(s.riv, kc[6 * kStride], q_in) : (s.riv - q) + q_in;
+    o.q_riv = q;
 }
 
 }  // namespace smart

@@ -250,3 +250,24 @@ def fma_peak(precision=64, blocks=None, threads=256, iters=1 << 16, repeats=5, d
                 best = min(best, e0.elapsed_time(e1))
     fmas = blocks * threads * 8 * iters
     return fmas / (best * 1e-3), best
+
+
+def score_series(simulation, observation, device=None):
+    """NSE, KGE, KGEc, KGEa, KGEb, PBias, RMSE of one simulated series against observations
+    with NaN = missing (montecarlo.py:193-203), computed on the device by
+    ``smart_score_discharge``.  Returns a list of 7 floats."""
+    torch = _torch()
+    dev = _require_cuda(device)
+    lib = _native.load()
+    sim = torch.as_tensor(np.ascontiguousarray(simulation, dtype=np.float64)).to(dev).reshape(-1, 1).contiguous()
+    obs = torch.as_tensor(np.ascontiguousarray(observation, dtype=np.float64)).to(dev).reshape(-1, 1).contiguous()
+    if sim.shape != obs.shape:
+        raise ValueError("simulation and observation must have the same length")
+    stats = torch.empty((1, _native.OBS_STATS), dtype=torch.float64, device=dev)
+    out = torch.empty((1, _native.N_SCORES), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _native.check(lib.smart_obs_stats(obs.data_ptr(), obs.shape[0], 1, stats.data_ptr(), stream))
+        _native.check(lib.smart_score_discharge(sim.data_ptr(), 1, 1, sim.shape[0], obs.data_ptr(),
+                                                stats.data_ptr(), 1, 1, 64, out.data_ptr(), stream))
+    return out[0, :7].cpu().tolist()

@@ -1,0 +1,284 @@
+"""CPU: the host side of the drop-in API (no compute calls): time frames, rescaling, file
+readers, parameters, settings, LHS sampler, conditioning, sharding, the C-ABI library."""
+import ctypes
+import os
+import re
+import subprocess
+from datetime import datetime, timedelta
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, ROOT
+
+
+# ---------------------------------------------------------------- files materialised from the raw fixture
+@pytest.fixture(scope="module")
+def catchment_dir(tmp_path_factory):
+    from smartpy_b200.timeframe import from_seconds
+    raw = load_golden("catchment_raw")
+    root = tmp_path_factory.mktemp("smart")
+    d = root / "in" / "Catchment"
+    d.mkdir(parents=True)
+    for name in ("rain", "peva", "flow"):
+        with open(d / ("Catchment." + name), "w") as f:
+            f.write("DateTime,%s\n" % name)
+            for t, v in zip(raw[name + "_t"], raw[name + "_v"]):
+                f.write("%s,%s\n" % (from_seconds(t).strftime("%Y-%m-%d %H:%M:%S"),
+                                     "" if np.isnan(v) else repr(float(v))))
+    with open(d / "Catchment.parameters", "w") as f:
+        f.write("PAR_NAME,PAR_VALUE\n")
+        for n, v in zip(['T', 'C', 'H', 'D', 'S', 'Z', 'SK', 'FK', 'GK', 'RK'], raw["parameters"]):
+            f.write("%s,%r\n" % (n, float(v)))
+    with open(d / "Catchment.sttngs", "w") as f:
+        f.write("ARGUMENT,VALUE\n")
+        for k, v in zip(raw["sttngs_keys"], raw["sttngs_vals"]):
+            f.write("%s,%s\n" % (k, v))
+    return str(root)
+
+
+@pytest.fixture(scope="module")
+def model(catchment_dir):
+    import smartpy_b200
+    return smartpy_b200.SMART('Catchment', 175.46e6, datetime(2007, 1, 1, 9), datetime(2016, 12, 31, 9),
+                              timedelta(hours=1), timedelta(days=1), 365, 'csv', 'csv', catchment_dir,
+                              gauged_area_m2=175.97e6)
+
+
+def test_smart_ingest_matches_reference_bit_for_bit(model):
+    """SMART.__init__ (smart.py:125-143): forcing disaggregation daily -> hourly and the
+    observation rescaling must reproduce the reference's arrays exactly."""
+    from smartpy_b200.timeframe import to_seconds
+    proc = load_golden("catchment_processed")
+    assert np.array_equal(model.nd_rain, np.repeat(proc["rain_hourly_per_day"], 24))
+    assert np.array_equal(model.nd_peva, np.repeat(proc["peva_hourly_per_day"], 24))
+    assert np.array_equal(model.nd_flow, proc["nd_flow"], equal_nan=True)
+    assert len(model.timeseries) == int(proc["simu_len"]) and len(model.timeseries_report) == int(proc["save_len"])
+    assert to_seconds(model.timeseries[0]) == int(proc["simu_first"])
+    assert to_seconds(model.timeseries[-1]) == int(proc["simu_last"])
+    assert to_seconds(model.timeseries_report[0]) == int(proc["save_first"])
+    assert to_seconds(model.timeseries_report[-1]) == int(proc["save_last"])
+    assert model.nd_rain[0] == model.nd_rain[23]            # a daily total split in 24 equal parts
+    assert len(model.flow) == 3653 and list(model.flow)[0] == datetime(2007, 1, 1, 9)
+    assert model.rain[model.timeseries[1]] == model.nd_rain[0]
+
+
+def test_smart_api_surface(model, catchment_dir):
+    import smartpy_b200
+    assert smartpy_b200.__version__
+    assert smartpy_b200.objfunctions.groundwater_constraint([0.5], [0.45]) == 1.0
+    assert smartpy_b200.objfunctions.groundwater_constraint([0.5], [0.61]) == 0.0
+    model.parameters.set_parameters_with_file(os.path.join(catchment_dir, 'in', 'Catchment', 'Catchment.parameters'))
+    assert model.parameters.names == ['T', 'C', 'H', 'D', 'S', 'Z', 'SK', 'FK', 'GK', 'RK']
+    assert np.array_equal(model.parameters.as_row(), load_golden("catchment_raw")["parameters"])
+    assert model.parameters.ranges['GK'] == (1200.0, 4800.0)
+    with pytest.raises(Exception, match="simulate"):
+        model.get_simulation_array()
+    assert model.get_evaluation_array() is model.nd_flow
+    with pytest.raises(Exception, match="modelled flow"):
+        model.write_output_files('modelled')
+    model.write_output_files('observed')
+    with open(os.path.join(model.out_f, 'Catchment.obs.flow')) as f:
+        lines = f.read().splitlines()
+    assert lines[0] == 'DateTime,flow' and len(lines) == 3654
+    assert lines[1] == '2007-01-01 09:00:00,%e' % model.nd_flow[0]
+
+
+def test_no_cpu_fallback(model):
+    """Without a GPU the product path must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    model.parameters.set_parameters_with_dict(dict(zip(model.parameters.names, load_golden("catchment_raw")["parameters"])))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.simulate(model.parameters.values)
+
+
+def test_parameters_errors(tmp_path):
+    from smartpy_b200.parameters import Parameters
+    p = Parameters()
+    with pytest.raises(Exception, match="no parameters file"):
+        p.set_parameters_with_file(str(tmp_path / "missing.parameters"))
+    f = tmp_path / "x.parameters"
+    f.write_text("PAR_NAME,PAR_VALUE\nT,1.0\nC,abc\n")
+    with pytest.raises(Exception, match="incorrect parameter value"):
+        p.set_parameters_with_file(str(f))
+    f.write_text("PAR_NAME,PAR_VALUE\nT,1.0\n")
+    with pytest.raises(Exception, match="parameter C is not available"):
+        p.set_parameters_with_file(str(f))
+    f.write_text("NAME,VALUE\nT,1.0\n")
+    with pytest.raises(Exception, match="PAR_NAME"):
+        p.set_parameters_with_file(str(f))
+    with pytest.raises(Exception, match="not available in the dictionary"):
+        p.set_parameters_with_dict({'T': 1.0})
+
+
+def test_settings_file(catchment_dir, tmp_path):
+    from smartpy_b200.inout import get_dict_simulation_settings
+    s = get_dict_simulation_settings(os.path.join(catchment_dir, 'in', 'Catchment', 'Catchment.sttngs'))
+    assert s == (175.46 * 1e6, 175.97 * 1e6, datetime(2007, 1, 1, 9), datetime(2016, 12, 31, 9),
+                 timedelta(hours=1), timedelta(days=1), 365, 0.12667)
+    f = tmp_path / "a.sttngs"
+    f.write_text("ARGUMENT,VALUE\ncatchment_area_km2,10\nstart_datetime,01/01/2007 09:00:00\n"
+                 "end_datetime,02/01/2007 09:00:00\nsimu_timedelta_min,60\nreport_timedelta_min,1440\nwarm_up_days,0\n")
+    s = get_dict_simulation_settings(str(f))
+    assert s[1] == s[0] == 10e6 and s[-1] is None
+    f.write_text("ARGUMENT,VALUE\ncatchment_area_km2,ten\n")
+    with pytest.raises(Exception, match="CATCHMENT AREA could not be converted"):
+        get_dict_simulation_settings(str(f))
+    f.write_text("ARGUMENT,VALUE\ncatchment_area_km2,10\n")
+    with pytest.raises(Exception, match="START is missing"):
+        get_dict_simulation_settings(str(f))
+
+
+# ---------------------------------------------------------------- time frames
+def test_timeframe_series():
+    from smartpy_b200.timeframe import TimeFrame
+    tf = TimeFrame(datetime(2007, 1, 1, 9), datetime(2007, 1, 3, 9), timedelta(hours=1), timedelta(days=1))
+    assert tf.get_series_save() == [datetime(2006, 12, 31, 9), datetime(2007, 1, 1, 9), datetime(2007, 1, 2, 9),
+                                    datetime(2007, 1, 3, 9)]
+    simu = tf.get_series_simu()
+    assert simu[0] == datetime(2006, 12, 31, 9) and simu[1] == datetime(2006, 12, 31, 10)
+    assert simu[-1] == datetime(2007, 1, 3, 9) and len(simu) == 73
+    assert tf.get_simu_length() == 72 and tf.get_report_gap() == 24
+    assert tf.get_gap_simu() == timedelta(hours=1) and tf.get_gap_report() == timedelta(days=1)
+    with pytest.raises(Exception, match="Save Start is greater"):
+        TimeFrame(datetime(2007, 1, 2), datetime(2007, 1, 1), timedelta(hours=1), timedelta(days=1))
+    with pytest.raises(Exception, match="not compatible"):
+        TimeFrame(datetime(2007, 1, 1), datetime(2007, 1, 2, 5), timedelta(hours=1), timedelta(days=1))
+    with pytest.raises(Exception, match="multiple of Simulation Gap"):
+        TimeFrame(datetime(2007, 1, 1), datetime(2007, 1, 2), timedelta(hours=5), timedelta(days=1))
+
+
+def test_cumulative_rescaling_dict_api_agrees_with_array_core():
+    from smartpy_b200 import timeframe as tfm
+    day, hour = timedelta(days=1), timedelta(hours=1)
+    start = datetime(2000, 1, 1, 9)
+    vals = {start + k * day: float(k + 1) * 0.37 for k in range(6)}
+    hi = tfm.increase_time_resolution_of_regular_cumulative_data(vals, start, start + 5 * day, day, hour)
+    assert len(hi) == 6 * 24
+    assert hi[start] == hi[start - 23 * hour] == 0.37 / 24
+    lo = tfm.decrease_time_resolution_of_regular_cumulative_data(hi, start + day, start + 5 * day, day, hour)
+    total = 0.0
+    for _ in range(24):
+        total += 2 * 0.37 / 24
+    assert lo[start + day] == total                         # sequential re-aggregation, same order
+    # 6-hourly simulation from daily data, shifted start: resolution = gcd(shift, gcd(24 h, 6 h))
+    res = tfm.get_required_resolution(start, start - 18 * hour, day, 6 * hour)
+    assert res == 6 * hour
+    out = tfm.rescale_time_resolution_of_regular_cumulative_data(
+        vals, start, start + 5 * day, day, res, start - 18 * hour, start + 5 * day, 6 * hour)
+    assert out[start - 18 * hour] == 0.37 / 4 and out[start + 5 * day] == 6 * 0.37 / 4
+    with pytest.raises(Exception, match="not multiples"):
+        tfm.increase_time_resolution_of_regular_cumulative_data(vals, start, start + day, day, timedelta(hours=5))
+    with pytest.raises(KeyError):
+        tfm.rescale_time_resolution_of_regular_cumulative_data(
+            vals, start, start + 5 * day, day, hour, start - 2 * day, start, hour)
+
+
+def test_mean_data_rescaling_gaps_and_missing():
+    from smartpy_b200 import timeframe as tfm
+    from collections import OrderedDict
+    day, hour = timedelta(days=1), timedelta(hours=1)
+    t0 = datetime(2007, 1, 1, 0)
+    obs = OrderedDict()
+    for k, v in ((0, 1.0), (1, 2.0), (2, 3.0), (5, 6.0), (6, 7.0)):    # days 3 and 4 missing
+        obs[t0 + k * day] = v
+    out = tfm.rescale_time_resolution_of_irregular_mean_data(obs, t0 + 9 * hour, t0 + 9 * hour + 6 * day, day, hour)
+    vals = list(out.values())
+    # report stamp D 09:00 averages D-1 10:00 .. D 09:00: 15 h of the value stamped D 00:00 and
+    # 9 h of the value stamped D+1 00:00 (replicated backwards); any uncovered hour -> NaN
+    assert vals[0] == (15 * 1.0 + 9 * 2.0) / 24 and vals[1] == (15 * 2.0 + 9 * 3.0) / 24
+    assert vals[5] == (15 * 6.0 + 9 * 7.0) / 24
+    assert all(np.isnan(vals[k]) for k in (2, 3, 4, 6))
+    ref = tfm.decrease_time_resolution_of_irregular_mean_data(
+        tfm.increase_time_resolution_of_irregular_mean_data(obs, day, hour),
+        t0 + 9 * hour, t0 + 9 * hour + 6 * day, hour, day)
+    assert np.array_equal(np.array(vals), np.array(list(ref.values())), equal_nan=True)
+
+
+def test_interval_checks():
+    from smartpy_b200.timeframe import check_interval_in_list
+    day = timedelta(days=1)
+    t0 = datetime(2000, 1, 1)
+    assert check_interval_in_list([t0, t0 + day, t0 + 2 * day], "f") == (t0, t0 + 2 * day, day)
+    with pytest.raises(Exception, match="Inconsistent Interval"):
+        check_interval_in_list([t0, t0 + day, t0 + 3 * day], "f")
+
+
+# ---------------------------------------------------------------- Monte Carlo host logic
+def test_lhs_sampler_reproduces_reference_stream():
+    from smartpy_b200.montecarlo.lhs import latin_hypercube
+    from smartpy_b200.parameters import Parameters
+    p = Parameters()
+    bounds = [p.ranges[n] for n in p.names]
+    np.random.seed(42)
+    sample = latin_hypercube(24, bounds)
+    assert np.array_equal(sample, load_golden("runs_members")["lhs24_seed42"])
+    # stratification: every column has exactly one value in each of the N strata
+    big = latin_hypercube(1000, bounds, rng=np.random.RandomState(1))
+    for k, (lo, hi) in enumerate(bounds):
+        strata = np.floor((big[:, k] - lo) / (hi - lo) * 1000).astype(int)
+        assert sorted(strata.tolist()) == list(range(1000))
+
+
+def test_conditioning_rules():
+    from smartpy_b200.montecarlo.glue import GLUE
+    from smartpy_b200.montecarlo.best import Best
+    params = np.arange(50, dtype=np.float32).reshape(5, 10)
+    fns = np.array([[0.1, 5.0], [0.5, 3.0], [0.7, 1.0], [0.9, 9.0], [0.3, 2.0]], dtype=np.float32)
+    keep = GLUE._get_behavioural_sets(params, fns, [(0.3,), (1.5, 6.0)], ['min', 'inside'])
+    assert np.array_equal(keep, params[[1, 4]])
+    keep = GLUE._get_behavioural_sets(params, fns[:, :1], [(0.5,)], ['max'])
+    assert np.array_equal(keep, params[[0, 1, 4]])
+    with pytest.raises(Exception, match="inconsistent"):
+        GLUE._get_behavioural_sets(params, fns[:, :1], [(2.0, 1.0)], ['inside'])
+    with pytest.raises(Exception, match="not in the database"):
+        GLUE._get_behavioural_sets(params, fns[:, :1], [(2.0,)], ['above'])
+    best = Best._get_best_sets(params, fns[:, 1:], [(8.0,)], ['max'], fns[:, :1], 2)
+    assert np.array_equal(best, params[[1, 2]])              # ascending by target, best last
+    with pytest.raises(Exception, match="restrained sample size"):
+        Best._get_best_sets(params, fns[:, 1:], [(2.5,)], ['max'], fns[:, :1], 3)
+
+
+def test_shard_bounds_cover_rows_once():
+    from smartpy_b200.distributed import shard_bounds
+    for n, world in ((10, 3), (8, 8), (5, 8), (10 ** 7, 8), (1, 2)):
+        spans = [shard_bounds(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+# ---------------------------------------------------------------- the C ABI library
+def test_library_exports_every_declared_symbol():
+    from smartpy_b200 import _native, _build
+    _build.build()
+    lib = _native.load()
+    header = open(os.path.join(ROOT, "include", "smart_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|size_t|const char \*)\s*\*?\s*(smart_\w+)\(", header, flags=re.M))
+    assert declared == set(_native.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.smart_version() == 100
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    d = _native.BatchDesc()
+    assert lib.smart_batch_run_f64(ctypes.byref(d), None) == _native.ERR_BAD_ARG
+    assert "n_members" in _native.last_error()
+
+
+def test_descriptor_layout_matches_header(tmp_path):
+    """ctypes mirror vs the C struct: size and every field offset, checked with gcc."""
+    from smartpy_b200 import _native
+    fields = [f[0] for f in _native.BatchDesc._fields_]
+    src = tmp_path / "layout.c"
+    body = "\n".join('printf("%s %%zu\\n", offsetof(smart_batch_desc, %s));' % (f, f) for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "smart_b200.h"\nint main(void){\n'
+                   'printf("sizeof %%zu\\n", sizeof(smart_batch_desc));\n%s\nreturn 0;}\n' % body)
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(_native.BatchDesc)
+    for f in fields:
+        assert int(out[f]) == getattr(_native.BatchDesc, f).offset, f

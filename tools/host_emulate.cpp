@@ -1,0 +1,68 @@
+// tools/host_emulate.cpp -- development aid: compile smart_step.cuh for the HOST (g++) to study
+// the rounding behaviour of the step formulations against the golden fixtures without a GPU.
+// Not part of the product and not an execution path of smartpy_b200 (which has no CPU fallback).
+//
+//   g++ -O2 -ffp-contract=off -DSMART_HOST_EMULATION -shared -fPIC -o build_exp/libemul.so tools/host_emulate.cpp
+#include <cmath>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline int __double2hiint(double x) { long long v; std::memcpy(&v, &x, 8); return (int)(v >> 32); }
+static inline int __float_as_int(float x) { int v; std::memcpy(&v, &x, 4); return v; }
+using std::fma;
+#include "../smartpy_b200/csrc/smart_step.cuh"
+
+using namespace smart;
+
+// mode 0: general, 1: fast (first form), 2: fast V2.  Mirrors run_member/run_timeline of
+// smart_kernels.cu for one member, summary or raw reporting.
+extern "C" int emulate_run(int mode, double area, double dt, long T, long W, const double *rain,
+                           const double *peva, const double *par, int has_extra, double aar_ro,
+                           const double *split, int report_type, int gap, double *discharge, double *gw_out)
+{
+    typedef double R;
+    const double Tt = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
+    const double SK = par[6], FK = par[7], GK = par[8], RK = par[9];
+    MemberPar<R> p;
+    p.Td = Tt; p.C = C; p.D = D; p.omD = 1.0 - D; p.Hz = H / Z; p.Sz = S / Z; p.z = Z / 6.0;
+    p.r_sk = dt / (SK * 3600.0); p.r_fk = dt / (FK * 3600.0); p.r_gk = dt / (GK * 3600.0); p.r_rk = dt / (RK * 3600.0);
+    R kc[7] = {C, D, 1.0 - D, 1.0 - p.r_sk, 1.0 - p.r_fk, 1.0 - p.r_gk, 1.0 - p.r_rk};
+    const double to_mm = 1e3 / area;
+    double v[12];
+    const double kk[5] = {SK, SK, FK, GK, GK};
+    for (int k = 0; k < 5; ++k) v[k] = has_extra ? aar_ro * split[k] / 1000 * area / 8766 * kk[k] : 0.0;
+    v[11] = has_extra ? aar_ro / 1000 * area / 8766 * RK : 0.0;
+    for (int k = 0; k < 6; ++k) v[5 + k] = (Z / 12) / 1000 * area;
+    MemberState<R> s;
+    s.ove = v[0] * to_mm; s.dra = v[1] * to_mm; s.itf = v[2] * to_mm; s.sgw = v[3] * to_mm; s.dgw = v[4] * to_mm;
+    for (int k = 0; k < 6; ++k) s.ly[k] = v[5 + k] * to_mm;
+    s.riv = v[11] * to_mm;
+    if (mode != 0) { s.ove += s.dra; s.sgw += s.dgw; s.dra = s.dgw = 0; }
+    FastCarry<R> carry; carry.tot = 0; carry.valid = false;
+    StepOut<R> o;
+    const R qscale = area / (1e3 * dt), mean_scale = area / (1e3 * dt) / (double)gap;
+    long n_rep = report_type == 1 ? T / gap : (T + gap - 1) / gap;
+    int countdown = 0x7fffffff; long r = 0;
+    R acc = 0, agw = 0, aall = 0; double GN = 0, GD = 0;
+    for (long seg = 0; seg < 2; ++seg) {
+        long n = seg == 0 ? W : T;
+        if (seg == 1) { countdown = (int)(T - (n_rep - 1) * gap); r = 0; acc = agw = aall = 0; GN = GD = 0; }
+        for (long i = 0; i < n; ++i) {
+            if (mode == 0) smart_step<R, true, false>(s, p, rain[i], peva[i], o);
+            else if (mode == 1) smart_step<R, false, false>(s, p, rain[i], peva[i], o);
+            else smart_step_fast<R, 1>(s, p, kc, carry, rain[i], peva[i], o);
+            acc += o.q_riv; agw += o.q_gw; aall += o.q_all;
+            if (--countdown == 0) {
+                countdown = gap;
+                R sval;
+                if (report_type == 1) sval = acc * mean_scale; else { sval = o.q_riv * qscale; agw = o.q_gw; aall = o.q_all; }
+                GN += agw; GD += aall; acc = agw = aall = 0;
+                discharge[r++] = sval;
+            }
+        }
+    }
+    *gw_out = GN / GD;
+    return 0;
+}
