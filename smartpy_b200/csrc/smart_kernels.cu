@@ -30,7 +30,10 @@ constexpr int kAccSlots = 7;       // per-thread binary64 accumulators parked in
 constexpr int kConstSlots = 7;     // per-thread constants of the fast step parked in smem
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
 #ifndef SMART_FAST_REGS_F64
-#define SMART_FAST_REGS_F64 88     // register budget of the fast FP64 kernel: 23 warps per SM
+#define SMART_FAST_REGS_F64 96     // register budget of the fast FP64 kernel (sweep 80..104 in profiles/): 20 warps per SM, no spills
+#endif
+#ifndef SMART_FAST_REGS_F32
+#define SMART_FAST_REGS_F32 64     // fast FP32 kernel: 32 warps per SM
 #endif
 
 thread_local std::string g_err;
@@ -445,8 +448,8 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 // all of its members qualify for the merged form and runs in exactly one of the two launches;
 // in the other it exits at once.  Separate kernels keep the fast variant's register count
 // (and so its occupancy) independent of the branch-faithful code.
-template <typename R, int kVariant, int BLOCK, int MIN_BLOCKS>
-__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS) smart_batch_kernel(const KArgs a)
+template <typename R, int kVariant, int BLOCK, int MAX_REGS>
+__global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -746,8 +749,9 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     }
     const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(a.chunk) * a.kc + kAccSlots * block) +
                         sizeof(R) * kConstSlots * block;
-    // fast kernel: register budget -> resident CTAs per SM (FP64: 88 regs = 23 warps; FP32: 64 regs = 32 warps)
-    constexpr int kFastWarps = sizeof(R) == 8 ? 65536 / (SMART_FAST_REGS_F64 * 32) : 32;
+    // register budgets: the fast kernel trades a few registers for resident warps
+    constexpr int kFastRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64 : SMART_FAST_REGS_F32;
+    constexpr int kSlowRegs = 128;
     const int variant = d->last_state ? kVariantFluxes : -1;
     auto go = [&](auto kernel) -> int {
         kernel<<<blocks, block, smem, stream>>>(a);
@@ -756,19 +760,19 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     };
     if (block == kBlockLarge) {
         if (variant == kVariantFluxes) {
-            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockLarge, 1>))) return rc;
+            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockLarge, kSlowRegs>))) return rc;
         } else {
             if (!a.force_general && !d->initial_state)
-                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockLarge, kFastWarps / 4>))) return rc;
-            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockLarge, 1>))) return rc;
+                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockLarge, kFastRegs>))) return rc;
+            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockLarge, kSlowRegs>))) return rc;
         }
     } else {
         if (variant == kVariantFluxes) {
-            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockSmall, 1>))) return rc;
+            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockSmall, kSlowRegs>))) return rc;
         } else {
             if (!a.force_general && !d->initial_state)
-                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockSmall, kFastWarps / 2>))) return rc;
-            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockSmall, 1>))) return rc;
+                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockSmall, kFastRegs>))) return rc;
+            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockSmall, kSlowRegs>))) return rc;
         }
     }
     if (d->best_sign != 0) {

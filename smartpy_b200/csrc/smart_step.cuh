@@ -217,6 +217,19 @@ struct FastCarry {
     bool valid;
 };
 
+// Soil total, left to right like the reference's sum() (structure.py:350).  SMART_TOT_TREE
+// switches to a depth-3 tree (same five additions, 25 instead of 41 cycles of dependent
+// latency); measured on B200 it makes no difference, so the reference's order is the default.
+template <typename R>
+__device__ __forceinline__ R soil_total(const MemberState<R> &s)
+{
+#ifndef SMART_TOT_TREE
+    return ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+#else
+    return ((s.ly[0] + s.ly[1]) + (s.ly[2] + s.ly[3])) + (s.ly[4] + s.ly[5]);
+#endif
+}
+
 __device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
 __device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >= 0; }
 
@@ -232,19 +245,28 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const MemberP
 
     if (ex_d >= 0.0) {
         R tot = carry.tot;
-        if (!carry.valid) tot = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+        if (!carry.valid) tot = soil_total(s);
         const R ex = static_cast<R>(ex_d);
         in_quick = (p.Hz * tot) * ex;                   // :363-364
         const R u0 = in_quick - ex;                     // u = -(excess rain still to place) <= 0
         R u = u0;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {                   // :367-374
+        auto fill = [&](int i) {                        // :367-374
             const R w = s.ly[i] - u;                    // level if the layer took everything
             const R t = p.z - w;
             const bool fits = sign_clear(t);
             s.ly[i] = fits ? w : p.z;
             u = fits ? zero : t;
+            return fits;
+        };
+#ifndef SMART_NO_EARLY_OUT
+        // most often the first layer takes everything for every member of the warp
+        const bool done = fill(0);
+        if (__any_sync(__activemask(), !done)) {
+            fill(1); fill(2); fill(3); fill(4); fill(5);
         }
+#else
+        fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
+#endif
         in_quick = fma(kc[1 * kStride], -u, in_quick);  // + D * saturation excess (:376)
         in_int = kc[2 * kStride] * (-u);                // (1 - D) * saturation excess (:377)
         const R sp = p.Sz * tot;                        // :379
@@ -257,10 +279,10 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const MemberP
         pw[5] = pw[2] * pw[2];
         if (kLeakByDifference) {
             // soil total after the fill, summed like tot1/tot3 so that a zero leak gives exactly 0
-            const R tot_f = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+            const R tot_f = soil_total(s);
 #pragma unroll
             for (int i = 0; i < 6; ++i) s.ly[i] = fma(-s.ly[i], pw[i], s.ly[i]);            // :381-385
-            const R tot1 = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+            const R tot1 = soil_total(s);
             in_int += tot_f - tot1;
 #pragma unroll
             for (int i = 0; i < 6; ++i) {                                                   // :388-399
@@ -269,7 +291,7 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const MemberP
             }
 #pragma unroll
             for (int i = 5; i >= 0; --i) s.ly[i] = fma(-s.ly[i], pw[5 - i], s.ly[i]);
-            const R tot3 = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+            const R tot3 = soil_total(s);
             in_gw = tot1 - tot3;
             carry.tot = tot3;
             carry.valid = true;
@@ -297,13 +319,21 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const MemberP
     } else {
         R d = static_cast<R>(-ex_d);                    // :407-419
         const R C = kc[0];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
+        auto take = [&](int i) {
             const R t = s.ly[i] - d;
             const bool enough = sign_clear(t);          // level >= deficit
             s.ly[i] = enough ? t : zero;
             d = enough ? zero : C * (-t);
+            return enough;
+        };
+#ifndef SMART_NO_EARLY_OUT
+        const bool done = take(0);
+        if (__any_sync(__activemask(), !done)) {
+            take(1); take(2); take(3); take(4); take(5);
         }
+#else
+        take(0); take(1); take(2); take(3); take(4); take(5);
+#endif
         carry.valid = false;
     }
 
