@@ -50,6 +50,10 @@ METRIC = "member-timesteps/s"
 # faithful restatement (FMA = one instruction): 65.5 on a dry step, 135.5 on a wet step.
 I_DRY, I_WET = 65.5, 135.5
 
+# smart_batch_run_* launches the fast kernel and the general kernel back to back (each CTA runs
+# in exactly one of them, smart_kernels.cu)
+KERNELS_PER_RUN = 2
+
 # members each host worker simulates per CPU-arm step (C oracle: ~26 ms per 96k-step member)
 CPU_MEMBERS_PER_WORKER = 24
 
@@ -296,7 +300,7 @@ def main():
 
     def step_resident():
         res = eng.run(p_dev, discharge=w["discharge"], scores=scored, gw=True, out=out)
-        launches[0] += 1
+        launches[0] += KERNELS_PER_RUN
         if world > 1:
             block[:, :8] = res["scores"] if scored else 0.0
             block[:, 8] = res["gw"]
@@ -312,7 +316,7 @@ def main():
     def step_e2e():
         p_stage.copy_(p_pin, non_blocking=True)
         res = eng.run(p_stage, discharge=w["discharge"], scores=scored, gw=True, out=out)
-        launches[0] += 1
+        launches[0] += KERNELS_PER_RUN
         if scored:
             sc_pin.copy_(res["scores"], non_blocking=True)
         gw_pin.copy_(res["gw"], non_blocking=True)

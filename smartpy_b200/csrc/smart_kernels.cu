@@ -14,11 +14,13 @@
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -31,6 +33,9 @@ constexpr int kConstSlots = 7;     // per-thread constants of the fast step park
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
 #ifndef SMART_FAST_REGS_F64
 #define SMART_FAST_REGS_F64 96     // register budget of the fast FP64 kernel (sweep 80..104 in profiles/): 20 warps per SM, no spills
+#endif
+#ifndef SMART_FAST_REGS_F64_LEAN
+#define SMART_FAST_REGS_F64_LEAN 80   // lean budget: 25 warps per SM, a few bytes of spills
 #endif
 #ifndef SMART_FAST_REGS_F32
 #define SMART_FAST_REGS_F32 64     // fast FP32 kernel: 32 warps per SM
@@ -111,6 +116,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (spins > (1u << 26)) __trap();
 }
 
+// doubles per forcing stage: chunk rows + one padding row (the fast step reads one step ahead),
+// rounded to 128 bytes so that every stage is a valid cp.async.bulk destination
+__host__ __device__ __forceinline__ int stage_doubles(int chunk, int kc) { return ((chunk + 1) * kc + 15) & ~15; }
+
 // ------------------------------------------------------------------ shared-memory layout of one CTA
 //   [0, 128)                       two mbarriers (TMA stages), padded
 //   double rain[2][chunk * kc]     forcing stages
@@ -124,7 +133,7 @@ struct Smem {
     uint64_t *full;
     double *rain, *peva, *acc;
     R *kconst;
-    __device__ __forceinline__ Smem(unsigned char *raw, int tile)
+    __device__ __forceinline__ Smem(unsigned char *raw, int tile)   // tile = stage_doubles(chunk, kc)
     {
         full = reinterpret_cast<uint64_t *>(raw);
         rain = reinterpret_cast<double *>(raw + kSmemHeader);
@@ -135,13 +144,14 @@ struct Smem {
 };
 
 // ------------------------------------------------------------------ the time loop
-template <typename R, int kVariant, int BLOCK>
+template <typename R, int kVariant, int BLOCK, bool kSingle>
 __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
-                                             const Smem<R, BLOCK> &sm, long long m, bool active, int c, int col,
-                                             int c_base, double area, double &gw_out, StepOut<R> &o)
+                                             const FastPar<R> &fp_, const Smem<R, BLOCK> &sm, long long m, bool active,
+                                             int c, int col, int c_base, double area, double &gw_out, StepOut<R> &o)
 {
     constexpr bool kFast = kVariant == kVariantFast;
-    const int tile = a.chunk * a.kc;
+    const int kc = kSingle ? 1 : a.kc;
+    const int tile = stage_doubles(a.chunk, kc);
     const int tid = threadIdx.x;
     double &A = sm.acc[0 * BLOCK + tid];      // sum (s - ebar)
     double &B = sm.acc[1 * BLOCK + tid];      // sum (s - ebar)^2
@@ -152,7 +162,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     double &RIV0 = sm.acc[6 * BLOCK + tid];   // river store at the start of the main run
     const R *kconst = sm.kconst + tid;
 
-    const int chunk = a.chunk, kc = a.kc;
+    const int chunk = a.chunk;
     const int nWc = static_cast<int>((a.W + chunk - 1) / chunk);
     const int nTot = nWc + static_cast<int>((a.T + chunk - 1) / chunk);
     const bool summary = a.report_type == SMART_REPORT_SUMMARY;
@@ -226,11 +236,19 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         }
         const double *fr = sm.rain + b * tile + col;
         const double *fp = sm.peva + b * tile + col;
+        // wet/dry driver of the fast step, formed one step ahead of the state
+        double ex_next = kFast ? __dsub_rn(__dmul_rn(fr[0], fp_.Td), fp[0]) : 0.0;
         for (int i = 0; i < n; ++i) {
             if (kFast) {
-                smart_step_fast<R, BLOCK>(s, p, kconst, carry, fr[i * kc], fp[i * kc], o);
+                const double ex_d = ex_next;
+                fr += kc;
+                fp += kc;
+                ex_next = __dsub_rn(__dmul_rn(fr[0], fp_.Td), fp[0]);   // last step of a stage: padding row, unused
+                smart_step_fast<R, BLOCK>(s, fp_, kconst, carry, ex_d, o);
             } else {
-                smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[i * kc], fp[i * kc], o);
+                smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
+                fr += kc;
+                fp += kc;
                 aall += o.q_all;
             }
             acc += o.q_riv;
@@ -295,13 +313,13 @@ __device__ __forceinline__ void finish_scores(const double *st, double A, double
     sc[6] = sqrt(E / n);                                      // RMSE
 }
 
-template <typename R, int kVariant, int BLOCK>
+template <typename R, int kVariant, int BLOCK, bool kSingle>
 __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
                                            long long m, bool active, int c, int col, int c_base, double area)
 {
     constexpr bool kFast = kVariant == kVariantFast;
     const int tid = threadIdx.x;
-    const Smem<R, BLOCK> sm(smem_raw, a.chunk * a.kc);
+    const Smem<R, BLOCK> sm(smem_raw, stage_doubles(a.chunk, kSingle ? 1 : a.kc));
     const double T = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
     const double SK = par[6], FK = par[7], GK = par[8], RK = par[9];
     MemberPar<R> p;
@@ -318,15 +336,24 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
     p.r_fk = static_cast<R>(r_fk);
     p.r_gk = static_cast<R>(r_gk);
     p.r_rk = static_cast<R>(r_rk);
+    FastPar<R> fp_;
+    fp_.Td = T;
+    fp_.Hz = p.Hz;
+    fp_.Sz = p.Sz;
+    fp_.z = p.z;
+    fp_.c_sk = static_cast<R>(1.0 - r_sk);
+    fp_.c_fk = static_cast<R>(1.0 - r_fk);
+    fp_.c_gk = static_cast<R>(1.0 - r_gk);
+    fp_.c_rk = static_cast<R>(1.0 - r_rk);
     if (kFast) {
         R *kconst = sm.kconst + tid;
         kconst[0 * BLOCK] = p.C;
         kconst[1 * BLOCK] = p.D;
         kconst[2 * BLOCK] = p.omD;
-        kconst[3 * BLOCK] = static_cast<R>(1.0 - r_sk);
-        kconst[4 * BLOCK] = static_cast<R>(1.0 - r_fk);
-        kconst[5 * BLOCK] = static_cast<R>(1.0 - r_gk);
-        kconst[6 * BLOCK] = static_cast<R>(1.0 - r_rk);
+        kconst[3 * BLOCK] = p.r_sk;
+        kconst[4 * BLOCK] = p.r_fk;
+        kconst[5 * BLOCK] = p.r_gk;
+        kconst[6 * BLOCK] = p.r_rk;
     }
 
     // initial conditions in m3 exactly as the reference writes them, then to mm
@@ -361,7 +388,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 
     double gw = 0.0;
     StepOut<R> o;
-    run_timeline<R, kVariant, BLOCK>(a, s, p, sm, m, active, c, col, c_base, area, gw, o);
+    run_timeline<R, kVariant, BLOCK, kSingle>(a, s, p, fp_, sm, m, active, c, col, c_base, area, gw, o);
 
     // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
     double target = -CUDART_INF;
@@ -448,7 +475,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 // all of its members qualify for the merged form and runs in exactly one of the two launches;
 // in the other it exits at once.  Separate kernels keep the fast variant's register count
 // (and so its occupancy) independent of the branch-faithful code.
-template <typename R, int kVariant, int BLOCK, int MAX_REGS>
+template <typename R, int kVariant, int BLOCK, int MAX_REGS, bool kSingle>
 __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -473,7 +500,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         if ((need_general != 0) != (kVariant == kVariantGeneral)) return;   // the other launch owns this CTA
     }
 
-    const bool multi = a.C > 1;
+    constexpr bool multi = !kSingle;
     const int c = multi ? static_cast<int>(m / a.mpc) : 0;
     const int c_base = multi ? static_cast<int>((static_cast<long long>(blockIdx.x) * BLOCK) / a.mpc) : 0;
     const int col = c - c_base;
@@ -489,7 +516,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         __syncthreads();
     }
 
-    run_member<R, kVariant, BLOCK>(a, smem_raw, par, m, active, c, col, c_base, area);
+    run_member<R, kVariant, BLOCK, kSingle>(a, smem_raw, par, m, active, c, col, c_base, area);
 }
 
 __global__ void best_finalize_kernel(const double *blk_score, const long long *blk_index, int n_blocks, int sign,
@@ -747,33 +774,62 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.blk_best_score = static_cast<double *>(d->workspace);
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
-    const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(a.chunk) * a.kc + kAccSlots * block) +
+    const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(stage_doubles(a.chunk, a.kc)) + kAccSlots * block) +
                         sizeof(R) * kConstSlots * block;
-    // register budgets: the fast kernel trades a few registers for resident warps
-    constexpr int kFastRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64 : SMART_FAST_REGS_F32;
-    constexpr int kSlowRegs = 128;
-    const int variant = d->last_state ? kVariantFluxes : -1;
-    auto go = [&](auto kernel) -> int {
+    using Kernel = void (*)(const KArgs);
+    auto go = [&](Kernel kernel) -> int {
         kernel<<<blocks, block, smem, stream>>>(a);
         SMART_CUDA(cudaGetLastError());
         return SMART_OK;
     };
+    // Fast kernel: two register budgets are compiled.  The roomy one (no spills) is quicker per
+    // wave; the lean one keeps more CTAs resident, which wins when it saves the batch a ragged
+    // last wave (config C2: 1e5 members are 1.06 waves at 90 registers, 0.88 at 80).
+    constexpr int kLeanRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64_LEAN : SMART_FAST_REGS_F32;
+    constexpr int kRoomyRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64 : SMART_FAST_REGS_F32;
+    constexpr int kSlowRegs = 128;
+    Kernel fast_lean, fast_roomy, general, fluxes;
+    auto pick = [&](auto block_tag, auto single_tag) {
+        constexpr int B = decltype(block_tag)::value;
+        constexpr bool S = decltype(single_tag)::value;
+        fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S>;
+        fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S>;
+        general = smart_batch_kernel<R, kVariantGeneral, B, kSlowRegs, S>;
+        fluxes = smart_batch_kernel<R, kVariantFluxes, B, kSlowRegs, S>;
+    };
+    using BL = std::integral_constant<int, kBlockLarge>;
+    using BS = std::integral_constant<int, kBlockSmall>;
     if (block == kBlockLarge) {
-        if (variant == kVariantFluxes) {
-            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockLarge, kSlowRegs>))) return rc;
-        } else {
-            if (!a.force_general && !d->initial_state)
-                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockLarge, kFastRegs>))) return rc;
-            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockLarge, kSlowRegs>))) return rc;
-        }
+        if (a.C == 1) pick(BL{}, std::true_type{}); else pick(BL{}, std::false_type{});
     } else {
-        if (variant == kVariantFluxes) {
-            if ((rc = go(smart_batch_kernel<R, kVariantFluxes, kBlockSmall, kSlowRegs>))) return rc;
-        } else {
-            if (!a.force_general && !d->initial_state)
-                if ((rc = go(smart_batch_kernel<R, kVariantFast, kBlockSmall, kFastRegs>))) return rc;
-            if ((rc = go(smart_batch_kernel<R, kVariantGeneral, kBlockSmall, kSlowRegs>))) return rc;
+        if (a.C == 1) pick(BS{}, std::true_type{}); else pick(BS{}, std::false_type{});
+    }
+    if (d->last_state) {
+        if ((rc = go(fluxes))) return rc;
+    } else {
+        if (!a.force_general && !d->initial_state) {
+            Kernel fast = fast_roomy;
+            if (fast_lean != fast_roomy) {
+                int dev = 0, sms = 0, per_sm_lean = 0, per_sm_roomy = 0;
+                SMART_CUDA(cudaGetDevice(&dev));
+                SMART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                SMART_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lean, fast_lean, block, smem));
+                SMART_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_roomy, fast_roomy, block, smem));
+                // cost model: full waves at the measured steady rates (lean is ~6 % slower per
+                // member), a ragged last wave costs at least 40 % of a full one (latency bound)
+                auto cost = [&](int per_sm, double rate) {
+                    const double slots = static_cast<double>(per_sm) * sms;
+                    const double waves = blocks / slots;
+                    const double whole = floor(waves), frac = waves - whole;
+                    const double tail = frac == 0.0 ? 0.0 : (frac > 0.4 ? frac : 0.4);
+                    return (whole + (whole == 0.0 ? frac : tail)) * slots / rate;
+                };
+                if (per_sm_lean > 0 && per_sm_roomy > 0 && cost(per_sm_lean, 0.94) < cost(per_sm_roomy, 1.0))
+                    fast = fast_lean;
+            }
+            if ((rc = go(fast))) return rc;
         }
+        if ((rc = go(general))) return rc;
     }
     if (d->best_sign != 0) {
         best_finalize_kernel<<<1, 32, 0, stream>>>(a.blk_best_score, a.blk_best_index, blocks, d->best_sign,

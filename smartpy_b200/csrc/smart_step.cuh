@@ -209,8 +209,16 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
 //     total before/after (mass conserving by construction; absolute error of a few ulp of the
 //     soil total, i.e. ~1e-14 mm per wet step);
 //   * reservoirs advance with one FMA: V' = V * (1 - dt/k) + inflow, Q = V * (dt/k).
-// kc[] holds the per-member constants that are parked in shared memory:
-//   kc[0] = C, kc[1] = D, kc[2] = 1 - D, kc[3..6] = 1 - dt/k for SK, FK, GK, RK.
+// Registers hold what the end of the step needs (1 - dt/k, on the critical path of the store
+// updates); shared memory (kc[], one column per thread) holds what can be fetched early:
+//   kc[0] = C, kc[1] = D, kc[2] = 1 - D, kc[3..6] = dt/k for SK, FK, GK, RK.
+template <typename R>
+struct FastPar {
+    double Td;                    // T in binary64 for the wet/dry predicate
+    R Hz, Sz, z;                  // H / Z, S / Z, Z / 6
+    R c_sk, c_fk, c_gk, c_rk;     // 1 - dt / (k * 3600)   (binary64 form only)
+};
+
 template <typename R>
 struct FastCarry {
     R tot;          // soil total at the end of the previous step, valid iff that step was wet
@@ -233,15 +241,29 @@ __device__ __forceinline__ R soil_total(const MemberState<R> &s)
 __device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
 __device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >= 0; }
 
+// ex_d = rain * T - peva (structure.py:353-355, two separately rounded binary64 operations) is
+// formed by the caller one step ahead: it depends on the forcing only, which takes the
+// shared-memory load and two FP64 latencies off the head of every step.
 template <typename R, int kStride>
-__device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const MemberPar<R> &p, const R *kc,
-                                                FastCarry<R> &carry, double rain, double peva, StepOut<R> &o)
+__device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar<R> &p, const R *kc,
+                                                FastCarry<R> &carry, double ex_d, StepOut<R> &o)
 {
     constexpr bool kLeakByDifference = sizeof(R) == 8;
+    constexpr bool kOneFma = sizeof(R) == 8;
     const R zero = R(0);
-    const double rain_c = __dmul_rn(rain, p.Td);        // structure.py:353-359, exact
-    const double ex_d = __dsub_rn(rain_c, peva);
     R in_quick = zero, in_int = zero, in_gw = zero;
+
+    // Outflows leave from the OLD storage (structure.py:427-447, :487), so they and the whole
+    // river update do not wait for the soil: issue them first.  SK/SK and GK/GK stores merged.
+    const R q_quick = s.ove * kc[3 * kStride];
+    const R q_int = s.itf * kc[4 * kStride];
+    const R q_gw = s.sgw * kc[5 * kStride];
+    const R q = s.riv * kc[6 * kStride];
+    const R q_in = (q_quick + q_int) + q_gw;            // :254
+    s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - q) + q_in;   // :487-498, cap cannot fire
+    o.q_gw = q_gw;
+    o.q_all = q_in;
+    o.q_riv = q;
 
     if (ex_d >= 0.0) {
         R tot = carry.tot;
@@ -337,23 +359,12 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const MemberP
         carry.valid = false;
     }
 
-    // :427-450 with the SK/SK and GK/GK stores merged; :487-498 without the cap (cannot fire).
     // binary64 advances a store with one FMA, V' = V * (1 - dt/k) + inflow; in binary32 the
     // rounding of (1 - dt/k) would bias the recession constant by up to 1e-4, so the two-step
     // form V' = (V - Q) + inflow is kept there.
-    constexpr bool kOneFma = sizeof(R) == 8;
-    const R q_quick = s.ove * p.r_sk;
-    s.ove = kOneFma ? fma(s.ove, kc[3 * kStride], in_quick) : (s.ove - q_quick) + in_quick;
-    const R q_int = s.itf * p.r_fk;
-    s.itf = kOneFma ? fma(s.itf, kc[4 * kStride], in_int) : (s.itf - q_int) + in_int;
-    const R q_gw = s.sgw * p.r_gk;
-    s.sgw = kOneFma ? fma(s.sgw, kc[5 * kStride], in_gw) : (s.sgw - q_gw) + in_gw;
-    o.q_gw = q_gw;
-    const R q_in = (q_quick + q_int) + q_gw;            // :254
-    o.q_all = q_in;
-    const R q = s.riv * p.r_rk;
-    s.riv = kOneFma ? fma(s.riv, kc[6 * kStride], q_in) : (s.riv - q) + q_in;
-    o.q_riv = q;
+    s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - q_quick) + in_quick;
+    s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - q_int) + in_int;
+    s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
 }
 
 }  // namespace smart
