@@ -121,6 +121,15 @@ int smart_batch_run_f64(const smart_batch_desc *d, void *stream);
 int smart_batch_run_f32(const smart_batch_desc *d, void *stream);
 
 /*
+ * Daily -> sub-daily disaggregation of cumulative forcing on the device, exactly as
+ * smartpy/timeframe.py:167-186 does on the host: every low-resolution value is divided once by
+ * `repeat` (IEEE divide) and stamped on `repeat` consecutive steps.
+ * in[n_in][C] -> out[n_in * repeat][C].  Device pointers.
+ */
+int smart_disaggregate(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double *out,
+                       void *stream);
+
+/*
  * Objective functions of already simulated series (montecarlo.py:193-209 on its own):
  * discharge[n_report][ld] (double when precision == 64, float when 32) against
  * obs[n_report][C] -> scores[N][8] with the GW column left NaN.  Device pointers.

@@ -32,7 +32,7 @@ FLAG_NO_TMA = 0x2
 SYMBOLS = (
     "smart_version", "smart_last_error", "smart_batch_n_report", "smart_batch_workspace_bytes",
     "smart_obs_stats", "smart_batch_run_f64", "smart_batch_run_f32", "smart_score_discharge",
-    "smart_batch_run_host",
+    "smart_disaggregate", "smart_batch_run_host",
     "smart_allsteps_host", "smart_fma_peak_probe",
 )
 
@@ -113,6 +113,9 @@ def load():
     lib.smart_score_discharge.argtypes = [
         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int32, ctypes.c_int32, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.smart_disaggregate.restype = ctypes.c_int
+    lib.smart_disaggregate.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_void_p, ctypes.c_void_p]
     lib.smart_batch_run_host.restype = ctypes.c_int
     lib.smart_batch_run_host.argtypes = [pdesc, ctypes.c_int, ctypes.c_int]
     lib.smart_allsteps_host.restype = ctypes.c_int

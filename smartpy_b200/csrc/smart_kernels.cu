@@ -28,7 +28,7 @@ namespace {
 using namespace smart;
 
 constexpr int kChunkSingle = 512;  // forcing steps per smem stage, single catchment
-constexpr int kAccSlots = 7;       // per-thread binary64 accumulators parked in smem
+constexpr int kAccSlots = 8;       // per-thread binary64 accumulators parked in smem
 constexpr int kConstSlots = 7;     // per-thread constants of the fast step parked in smem
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
 #ifndef SMART_FAST_REGS_F64
@@ -108,6 +108,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Ampere-style asynchronous 8-byte copies (SASS LDGSTS) for the [t][catchment] tiles, whose rows
+// are too short (kc * 8 bytes) for the 16-byte granules of cp.async.bulk
+__device__ __forceinline__ void cp_async_8(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     // try_wait suspends in hardware up to a time limit; the bound only turns a lost copy
@@ -160,12 +173,15 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     double &GN = sm.acc[4 * BLOCK + tid];     // sum (Q_sgw + Q_dgw)
     double &GD = sm.acc[5 * BLOCK + tid];     // sum of the five pathway flows
     double &RIV0 = sm.acc[6 * BLOCK + tid];   // river store at the start of the main run
+    double &SCALE = sm.acc[7 * BLOCK + tid];  // mm per step -> m3/s (and / report_gap for 'summary')
     const R *kconst = sm.kconst + tid;
+    constexpr bool kWide = sizeof(R) == 8;    // binary64 state: run-long sums stay in registers
 
     const int chunk = a.chunk;
     const int nWc = static_cast<int>((a.W + chunk - 1) / chunk);
     const int nTot = nWc + static_cast<int>((a.T + chunk - 1) / chunk);
-    const bool summary = a.report_type == SMART_REPORT_SUMMARY;
+    // with one simulation step per reporting step 'raw' and 'summary' coincide (structure.py:190-195)
+    const bool summary = a.report_type == SMART_REPORT_SUMMARY || a.gap == 1;
 
     auto chunk_span = [&](int ci, long long &t0, int &n) {
         if (ci < nWc) {
@@ -196,6 +212,28 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         }
     };
 
+    // generic producer (every thread): rows t0..t0+n, columns c_base..c_base+kc of [T][C], as
+    // asynchronous copies so that the next stage loads while the current one is consumed
+    auto async_issue = [&](int ci) {
+        long long t0;
+        int n;
+        chunk_span(ci, t0, n);
+        double *dr = sm.rain + (ci & 1) * tile, *dp = sm.peva + (ci & 1) * tile;
+        for (int idx = tid; idx < n * kc; idx += BLOCK) {
+            const int row = idx / kc, cc = idx - row * kc;
+            const int cg = c_base + cc;
+            if (cg < a.C) {
+                const long long g = (t0 + row) * static_cast<long long>(a.C) + cg;
+                cp_async_8(dr + idx, a.rain + g);
+                cp_async_8(dp + idx, a.peva + g);
+            } else {
+                dr[idx] = 0.0;
+                dp[idx] = 0.0;
+            }
+        }
+        cp_async_commit();
+    };
+
     int countdown = 0x7fffffff;   // never fires during the warm-up
     int r = 0;
     R acc = R(0), agw = R(0), aall = R(0);
@@ -205,7 +243,11 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     o.q_riv = o.q_gw = o.q_all = R(0);
     o.aeva = o.q_ove = o.q_dra = o.q_int = o.q_sgw = o.q_dgw = R(0);
 
-    if (a.use_tma && tid == 0) tma_issue(0);
+    if (a.use_tma) {
+        if (tid == 0) tma_issue(0);
+    } else {
+        async_issue(0);
+    }
 
     for (int ci = 0; ci < nTot; ++ci) {
         const int b = ci & 1;
@@ -216,14 +258,11 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
             if (tid == 0 && ci + 1 < nTot) tma_issue(ci + 1);
             mbar_wait(&sm.full[b], static_cast<uint32_t>((ci >> 1) & 1));
         } else {
-            // coalesced tile load: rows t0..t0+n, columns c_base..c_base+kc of [T][C]
-            for (int idx = tid; idx < n * kc; idx += BLOCK) {
-                const int row = idx / kc, cc = idx - row * kc;
-                const int cg = c_base + cc;
-                const bool ok = cg < a.C;
-                const long long g = (t0 + row) * static_cast<long long>(a.C) + cg;
-                sm.rain[b * tile + idx] = ok ? a.rain[g] : 0.0;
-                sm.peva[b * tile + idx] = ok ? a.peva[g] : 0.0;
+            if (ci + 1 < nTot) {
+                async_issue(ci + 1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
             __syncthreads();
         }
@@ -233,6 +272,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
             acc = agw = aall = R(0);
             A = B = Cc = E = GN = GD = 0.0;
             RIV0 = static_cast<double>(s.riv);
+            SCALE = area / (1e3 * a.dt) / (summary ? static_cast<double>(a.gap) : 1.0);
         }
         const double *fr = sm.rain + b * tile + col;
         const double *fp = sm.peva + b * tile + col;
@@ -249,26 +289,30 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                 smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
                 fr += kc;
                 fp += kc;
-                aall += o.q_all;
             }
             acc += o.q_riv;
-            agw += o.q_gw;
+            // groundwater share (structure.py:191, :194-195): 'summary' sums every step, 'raw' only
+            // the sampled ones.  Fast form: the pathway total is recovered from the river's mass
+            // balance (sum q_in = sum q_out + dV_river), so only sum q_out is accumulated.
+            if (summary) {
+                agw += o.q_gw;
+                if (!kFast) aall += o.q_all;
+            }
             if (--countdown == 0) {
                 countdown = a.gap;
-                R sval;
+                const R sval = (summary ? acc : o.q_riv) * static_cast<R>(SCALE);   // structure.py:190 | :193
                 if (summary) {
-                    sval = acc * static_cast<R>(area / (1e3 * a.dt) / static_cast<double>(a.gap));   // structure.py:190
-                    // fast form: the pathway total is recovered from the river's mass balance at the
-                    // end (sum q_in = sum q_out + dV_river), so only sum q_out is accumulated here
-                    if (kFast) aall = acc;
+                    if (kFast) aall += acc;
                 } else {
-                    sval = o.q_riv * static_cast<R>(area / (1e3 * a.dt));                           // structure.py:193
-                    agw = o.q_gw;                            // :194-195 sample the same rows
-                    aall = o.q_all;
+                    agw += o.q_gw;
+                    aall += o.q_all;
                 }
-                GN += static_cast<double>(agw);
-                GD += static_cast<double>(aall);
-                acc = agw = aall = R(0);
+                acc = R(0);
+                if (!kWide) {   // binary32 state: fold the per-gap sums into binary64
+                    GN += static_cast<double>(agw);
+                    GD += static_cast<double>(aall);
+                    agw = aall = R(0);
+                }
                 if (a.discharge != nullptr && active)
                     static_cast<R *>(a.discharge)[static_cast<long long>(r) * a.ld_q + m] = sval;
                 if (a.obs != nullptr) {
@@ -289,9 +333,10 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         }
         __syncthreads();   // every thread is done with stage b before it is refilled
     }
-    double gd = GD;
+    double gn = kWide ? static_cast<double>(agw) : GN;
+    double gd = kWide ? static_cast<double>(aall) : GD;
     if (kFast && summary) gd += static_cast<double>(s.riv) - RIV0;
-    gw_out = GN / gd;
+    gw_out = gn / gd;
 }
 
 // Final objective functions from the shifted sums (montecarlo.py:199-203; formulas of
@@ -604,6 +649,19 @@ __global__ void obs_stats_kernel(const double *obs, long long n_report, int C, d
     }
 }
 
+// out[(i * repeat + k) * C + c] = in[i * C + c] / repeat   (timeframe.py:180-183)
+__global__ void disaggregate_kernel(const double *in, long long n_in, int C, int repeat, double *out)
+{
+    const long long total = n_in * repeat * C;
+    const double div = static_cast<double>(repeat);
+    for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < total;
+         j += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = j / C;
+        const int c = static_cast<int>(j - row * C);
+        out[j] = in[(row / repeat) * C + c] / div;
+    }
+}
+
 template <typename R>
 __global__ void score_discharge_kernel(const R *q, long long ld, long long N, long long n_report, const double *obs,
                                        const double *obs_stats, int C, int mpc, double *scores)
@@ -881,6 +939,20 @@ int smart_batch_run_f64(const smart_batch_desc *d, void *stream)
 int smart_batch_run_f32(const smart_batch_desc *d, void *stream)
 {
     return launch<float>(d, static_cast<cudaStream_t>(stream));
+}
+
+int smart_disaggregate(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double *out,
+                       void *stream)
+{
+    if (!in || !out || n_in < 1 || n_catchments < 1 || repeat < 1)
+        return fail(SMART_ERR_BAD_ARG, "smart_disaggregate: bad argument");
+    const long long total = static_cast<long long>(n_in) * repeat * n_catchments;
+    const int threads = 256;
+    const long long want = (total + threads - 1) / threads;
+    const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
+    disaggregate_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, n_in, n_catchments, repeat, out);
+    SMART_CUDA(cudaGetLastError());
+    return SMART_OK;
 }
 
 int smart_score_discharge(const void *discharge, int64_t ld_discharge, int64_t n_members, int64_t n_report,

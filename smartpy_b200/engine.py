@@ -50,7 +50,8 @@ class BatchEngine(object):
 
     def __init__(self, rain, peva, area_m2, delta_sec, report_gap, obs=None, extra=None,
                  warm_up_steps=0, report='summary', gw_constraint=None,
-                 members_per_catchment=None, precision='f64', device=None, flags=0):
+                 members_per_catchment=None, precision='f64', device=None, flags=0,
+                 forcing_repeat=1):
         torch = _torch()
         self.lib = _native.load()
         self.device = _require_cuda(device)
@@ -69,11 +70,16 @@ class BatchEngine(object):
         peva = torch.as_tensor(np.ascontiguousarray(peva, dtype=np.float64) if not torch.is_tensor(peva) else peva)
         if rain.shape != peva.shape:
             raise ValueError("rain and peva must have the same shape")
-        self.n_steps = int(rain.shape[0])
         self.n_catchments = 1 if rain.dim() == 1 else int(rain.shape[1])
         self.members_per_catchment = int(members_per_catchment) if members_per_catchment else 0
         self.rain = rain.to(self.device, torch.float64).contiguous()
         self.peva = peva.to(self.device, torch.float64).contiguous()
+        # forcing_repeat > 1: rain/peva are totals over `forcing_repeat` simulation steps (e.g. daily
+        # values for an hourly model); the equal split of timeframe.py:167-186 happens on the device
+        if int(forcing_repeat) > 1:
+            self.rain = self._disaggregate(self.rain, int(forcing_repeat))
+            self.peva = self._disaggregate(self.peva, int(forcing_repeat))
+        self.n_steps = int(self.rain.shape[0])
         area = np.atleast_1d(np.asarray(area_m2, dtype=np.float64))
         if area.shape != (self.n_catchments,):
             raise ValueError("area_m2 must have one value per catchment")
@@ -98,6 +104,16 @@ class BatchEngine(object):
                                               self.obs_stats.data_ptr(),
                                               torch.cuda.current_stream(self.device).cuda_stream)
             _native.check(rc)
+
+    def _disaggregate(self, coarse, repeat):
+        torch = _torch()
+        shape = (coarse.shape[0] * repeat,) + tuple(coarse.shape[1:])
+        fine = torch.empty(shape, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.smart_disaggregate(coarse.data_ptr(), coarse.shape[0], self.n_catchments, repeat,
+                                             fine.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        _native.check(rc)
+        return fine
 
     # ------------------------------------------------------------------ descriptor
     def _desc(self, n_members):

@@ -258,6 +258,25 @@ class MonteCarlo(object):
                         shutil.copyfileobj(f_in, f_out)
                 remove(self.db_file)
 
+    # ------------------------------------------------------------------ conditioning on the device
+    def select_behavioural(self, conditioning):
+        """GLUE's selection applied to the scores of the last run(), on the device: returns
+        (row indices tensor, parameter rows [M, 10] float64)."""
+        from .conditioning import behavioural_rows
+        if self.results is None:
+            raise Exception("No results to condition: call run() first.")
+        rows = behavioural_rows(self.results['scores'], self.obj_fn_names, conditioning)
+        return rows, self.sample_params[rows.cpu().numpy()]
+
+    def select_best(self, target, nb_best, constraining=None):
+        """Best's selection applied to the scores of the last run(), on the device (top-k): returns
+        (row indices tensor, parameter rows [nb_best, 10] float64), best last."""
+        from .conditioning import best_rows
+        if self.results is None:
+            raise Exception("No results to condition: call run() first.")
+        rows = best_rows(self.results['scores'], self.obj_fn_names, target, nb_best, constraining)
+        return rows, self.sample_params[rows.cpu().numpy()]
+
     # ------------------------------------------------------------------ reading a sample database back
     def _get_sampled_sets_from_file(self, file_location, param_names, obj_fn_names, decompression_csv):
         """-> (params float32 [N, 10], obj_fns float32 [N, k]) (montecarlo.py:233-262)."""

@@ -90,6 +90,12 @@ def test_run_mc_lhs(catchment_dir):  # noqa: F811
     assert np.max(np.abs(sim[0] - q_ref[0]) / q_ref[0]) < 1e-10
     of = setup.objectivefunction(sim, setup.evaluation())
     assert np.allclose(of, sc_ref[0], rtol=1e-9, atol=0)
+    # conditioning of the scores that are still on the device
+    rows, picked = setup.select_best('NSE', 2)
+    assert rows.tolist() == np.argsort(sc_ref[:, 0], kind='stable')[-2:].tolist()
+    assert np.array_equal(picked, setup.lhs_params[rows.cpu().numpy()])
+    rows, _ = setup.select_behavioural({'KGE': ('max', (float(np.median(sc_ref[:, 1])),))})
+    assert rows.tolist() == np.nonzero(sc_ref[:, 1] <= np.median(sc_ref[:, 1]))[0].tolist()
     # conditioning on top of that sample
     np.random.seed(42)
     montecarlo.LHS('Catchment', catchment_dir, 'csv', 'csv', sample_size=5).run()

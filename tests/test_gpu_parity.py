@@ -307,3 +307,51 @@ def test_batch_run_host_entry_point(catchment):
     q_ref, gw_ref = oracle.run_members(catchment.area, 3600.0, rain, peva, params, EXTRA, days * 24, 24, warm_up=30)
     assert relmax(q.T, q_ref) < RTOL_Q
     assert relmax(gw, gw_ref) < 1e-9
+
+
+# ---------------------------------------------------------------- daily forcing in, equal split on the device
+def test_device_disaggregation_is_bit_identical(catchment):
+    """forcing_repeat=24 (smart_disaggregate) must reproduce the host split of
+    timeframe.py:167-186 bit for bit, hence identical discharge."""
+    torch = _torch()
+    from smartpy_b200.engine import BatchEngine, warm_up_length
+    proc = load_golden("catchment_processed")
+    g = load_golden("runs_members")
+    days = 400
+    daily_rain = proc["rain_hourly_per_day"][:days] * 24.0     # not necessarily the raw totals: any daily series
+    daily_peva = proc["peva_hourly_per_day"][:days] * 24.0
+    kw = dict(extra=EXTRA, warm_up_steps=warm_up_length(30, 3600.0))
+    a = BatchEngine(np.repeat(daily_rain / 24.0, 24), np.repeat(daily_peva / 24.0, 24), catchment.area, 3600.0, 24, **kw)
+    b = BatchEngine(daily_rain, daily_peva, catchment.area, 3600.0, 24, forcing_repeat=24, **kw)
+    assert torch.equal(a.rain, b.rain) and torch.equal(a.peva, b.peva)
+    qa = a.run(g["params"], discharge=True, scores=False)["discharge"]
+    qb = b.run(g["params"], discharge=True, scores=False)["discharge"]
+    assert torch.equal(qa, qb)
+    # [t][catchment] layout
+    c = BatchEngine(np.stack([daily_rain, daily_rain * 0.5], 1), np.stack([daily_peva, daily_peva], 1),
+                    [catchment.area, 2 * catchment.area], 3600.0, 24, forcing_repeat=24, members_per_catchment=20, **kw)
+    assert torch.equal(c.rain[:, 0], a.rain) and torch.equal(c.rain[:, 1], torch.from_numpy(np.repeat(daily_rain * 0.5 / 24.0, 24)).to(c.rain.device))
+    qc = c.run(g["params"], discharge=True, scores=False)["discharge"]
+    assert torch.equal(qc[:, :20], qa[:, :20])
+
+
+def test_general_kernel_on_out_of_range_members(catchment, oracle_lib):
+    """Members outside the fast form's validity (S > 0.5, routing constants below dt, D > 1 ...)
+    are routed to the branch-faithful kernel CTA by CTA, inside one batch with in-range members."""
+    _torch()
+    g = load_golden("runs_members")
+    wild = np.array([
+        [1.0, 0.5, 0.2, 0.3, 1.5, 60.0, 0.5, 2.0, 30.0, 0.2],
+        [1.05, 0.9, 0.6, 0.5, 3.0, 20.0, 5.0, 10.0, 12.0, 3.0],
+        [0.95, 0.1, 0.1, 0.9, 0.9, 100.0, 30.0, 30.0, 30.0, 30.0],
+        [1.0, 0.5, 0.995, 1.0, 0.01, 50.0, 1.0, 48.0, 1200.0, 1.0],
+    ])
+    params = np.concatenate([g["params"][:70 % len(g["params"])], wild, np.resize(g["params"], (150, 10))])
+    n_steps = 24 * 300
+    eng = make_engine(catchment, n_steps=n_steps, obs=False, warm_up_days=20)
+    q = eng.run(params, discharge=True, scores=False)["discharge"].cpu().numpy().T
+    for m in list(range(28, 36)) + [0, 100, len(params) - 1]:
+        q_ref, _ = oracle_lib.run(catchment.area, 3600.0, catchment.rain[:n_steps], catchment.peva[:n_steps], params[m],
+                                  EXTRA, n_steps, 24, warm_up=20)
+        scale = np.maximum(np.abs(q_ref), 1e-9 * np.abs(q_ref).max())
+        assert np.max(np.abs(q[m] - q_ref) / scale) < RTOL_Q

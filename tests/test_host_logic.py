@@ -282,3 +282,42 @@ def test_descriptor_layout_matches_header(tmp_path):
     assert int(out["sizeof"]) == ctypes.sizeof(_native.BatchDesc)
     for f in fields:
         assert int(out[f]) == getattr(_native.BatchDesc, f).offset, f
+
+
+def test_device_conditioning_matches_reference_rules():
+    """conditioning.py on CPU tensors against the numpy rules kept in GLUE/Best."""
+    import torch
+    from smartpy_b200.montecarlo import conditioning
+    from smartpy_b200.montecarlo.glue import GLUE
+    from smartpy_b200.montecarlo.best import Best
+    rng = np.random.RandomState(3)
+    names = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
+    scores = rng.randn(500, 8)
+    scores[:, 7] = rng.rand(500) > 0.5
+    params = rng.rand(500, 10)
+    t = torch.from_numpy(scores)
+    cond = {'NSE': ('min', (0.2,)), 'PBias': ('inside', (-1.0, 1.0)), 'GW': ('equal', (1.0,))}
+    rows = conditioning.behavioural_rows(t, names, cond).numpy()
+    ref = GLUE._get_behavioural_sets(params, scores[:, [0, 5, 7]], [cond[k][1] for k in cond], [cond[k][0] for k in cond])
+    assert np.array_equal(params[rows], ref)
+    rows = conditioning.best_rows(t, names, 'KGE', 7, {'RMSE': ('max', (0.5,))}).numpy()
+    ref = Best._get_best_sets(params, scores[:, [6]], [(0.5,)], ['max'], scores[:, [1]], 7)
+    assert np.array_equal(params[rows], ref)
+    with pytest.raises(Exception, match="restrained sample size"):
+        conditioning.best_rows(t, names, 'KGE', 400, {'RMSE': ('max', (-5.0,))})
+    with pytest.raises(Exception, match="not recognised"):
+        conditioning.best_rows(t, names, 'XYZ', 1)
+
+
+def test_device_lhs_is_stratified():
+    import torch
+    from smartpy_b200.montecarlo.conditioning import latin_hypercube_device
+    from smartpy_b200.parameters import Parameters
+    p = Parameters()
+    bounds = [p.ranges[n] for n in p.names]
+    g = torch.Generator().manual_seed(5)
+    sample = latin_hypercube_device(2000, bounds, generator=g).numpy()
+    assert sample.shape == (2000, 10)
+    for k, (lo, hi) in enumerate(bounds):
+        strata = np.floor((sample[:, k] - lo) / (hi - lo) * 2000).astype(int)
+        assert sorted(strata.tolist()) == list(range(2000))
