@@ -396,6 +396,15 @@ def main():
     except (OSError, ValueError):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f).get("{}:{}".format(args.workload, n))
+        if t:
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {
         "bound": "fp64-pipe" if bits == 64 else "fp32-pipe",
         "achieved": achieved / 1e12, "peak": peak_fma / 1e12,
@@ -404,7 +413,8 @@ def main():
         "i_alg_per_member_step": i_alg, "wet_fraction": wfrac,
         "peak_source": "measured in this run: smart_fma_peak_probe (8 dependent FMA chains/thread, 256 thr x 8 CTA/SM)",
         "peak_nominal": 148 * (64 if bits == 64 else 128) * 1.965e9 / 1e12,
-        "traffic": None,
+        "traffic": traffic,
+        "algorithmic_bytes": hbm_bytes_per_step,
         "hbm": {"achieved_gbs": hbm_bytes_per_step / (ms_per_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": hbm_bytes_per_step / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},

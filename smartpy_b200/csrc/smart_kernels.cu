@@ -29,7 +29,7 @@ using namespace smart;
 
 constexpr int kChunkSingle = 512;  // forcing steps per smem stage, single catchment
 constexpr int kAccSlots = 8;       // per-thread binary64 accumulators parked in smem
-constexpr int kConstSlots = 7;     // per-thread constants of the fast step parked in smem
+constexpr int kConstSlots = 8;     // per-thread R-typed constants of the fast step parked in smem (7 used)
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
 #ifndef SMART_FAST_REGS_F64
 #define SMART_FAST_REGS_F64 96     // register budget of the fast FP64 kernel (sweep 80..104 in profiles/): 20 warps per SM, no spills
@@ -139,6 +139,7 @@ __host__ __device__ __forceinline__ int stage_doubles(int chunk, int kc) { retur
 //   double peva[2][chunk * kc]
 //   double acc[kAccSlots][BLOCK]   per-thread binary64 accumulators touched once per report step
 //   R      kconst[kConstSlots][BLOCK]  per-thread constants of the fast step (see smart_step_fast)
+//   double td[BLOCK]               parameter T in binary64 (wet/dry predicate)
 enum : int { kVariantFast = 0, kVariantGeneral = 1, kVariantFluxes = 2 };
 
 template <typename R, int BLOCK>
@@ -146,6 +147,7 @@ struct Smem {
     uint64_t *full;
     double *rain, *peva, *acc;
     R *kconst;
+    double *td;
     __device__ __forceinline__ Smem(unsigned char *raw, int tile)   // tile = stage_doubles(chunk, kc)
     {
         full = reinterpret_cast<uint64_t *>(raw);
@@ -153,6 +155,7 @@ struct Smem {
         peva = rain + 2 * tile;
         acc = peva + 2 * tile;
         kconst = reinterpret_cast<R *>(acc + kAccSlots * BLOCK);
+        td = reinterpret_cast<double *>(kconst + kConstSlots * BLOCK);
     }
 };
 
@@ -277,13 +280,15 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         const double *fr = sm.rain + b * tile + col;
         const double *fp = sm.peva + b * tile + col;
         // wet/dry driver of the fast step, formed one step ahead of the state
-        double ex_next = kFast ? __dsub_rn(__dmul_rn(fr[0], fp_.Td), fp[0]) : 0.0;
+        // (T sits in shared memory next to the other early-fetch constants; binary64 in both modes)
+        const double *tdp = sm.td + tid;
+        double ex_next = kFast ? __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]) : 0.0;
         for (int i = 0; i < n; ++i) {
             if (kFast) {
                 const double ex_d = ex_next;
                 fr += kc;
                 fp += kc;
-                ex_next = __dsub_rn(__dmul_rn(fr[0], fp_.Td), fp[0]);   // last step of a stage: padding row, unused
+                ex_next = __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]);   // last step of a stage: padding row, unused
                 smart_step_fast<R, BLOCK>(s, fp_, kconst, carry, ex_d, o);
             } else {
                 smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
@@ -302,7 +307,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                 countdown = a.gap;
                 const R sval = (summary ? acc : o.q_riv) * static_cast<R>(SCALE);   // structure.py:190 | :193
                 if (summary) {
-                    if (kFast) aall += acc;
+                    if (kFast) GD += static_cast<double>(acc);   // once per report step: lives in shared memory
                 } else {
                     agw += o.q_gw;
                     aall += o.q_all;
@@ -335,7 +340,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     }
     double gn = kWide ? static_cast<double>(agw) : GN;
     double gd = kWide ? static_cast<double>(aall) : GD;
-    if (kFast && summary) gd += static_cast<double>(s.riv) - RIV0;
+    if (kFast && summary) gd = GD + (static_cast<double>(s.riv) - RIV0);
     gw_out = gn / gd;
 }
 
@@ -382,7 +387,6 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
     p.r_gk = static_cast<R>(r_gk);
     p.r_rk = static_cast<R>(r_rk);
     FastPar<R> fp_;
-    fp_.Td = T;
     fp_.Hz = p.Hz;
     fp_.Sz = p.Sz;
     fp_.z = p.z;
@@ -399,6 +403,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         kconst[4 * BLOCK] = p.r_fk;
         kconst[5 * BLOCK] = p.r_gk;
         kconst[6 * BLOCK] = p.r_rk;
+        sm.td[tid] = T;
     }
 
     // initial conditions in m3 exactly as the reference writes them, then to mm
@@ -833,7 +838,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
     const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(stage_doubles(a.chunk, a.kc)) + kAccSlots * block) +
-                        sizeof(R) * kConstSlots * block;
+                        sizeof(R) * kConstSlots * block + sizeof(double) * block;
     using Kernel = void (*)(const KArgs);
     auto go = [&](Kernel kernel) -> int {
         kernel<<<blocks, block, smem, stream>>>(a);

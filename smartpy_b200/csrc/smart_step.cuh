@@ -214,7 +214,6 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
 //   kc[0] = C, kc[1] = D, kc[2] = 1 - D, kc[3..6] = dt/k for SK, FK, GK, RK.
 template <typename R>
 struct FastPar {
-    double Td;                    // T in binary64 for the wet/dry predicate
     R Hz, Sz, z;                  // H / Z, S / Z, Z / 6
     R c_sk, c_fk, c_gk, c_rk;     // 1 - dt / (k * 3600)   (binary64 form only)
 };

@@ -31,7 +31,7 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
     p.Td = Tt; p.C = C; p.D = D; p.omD = 1.0 - D; p.Hz = H / Z; p.Sz = S / Z; p.z = Z / 6.0;
     p.r_sk = dt / (SK * 3600.0); p.r_fk = dt / (FK * 3600.0); p.r_gk = dt / (GK * 3600.0); p.r_rk = dt / (RK * 3600.0);
     R kc[7] = {C, D, 1.0 - D, p.r_sk, p.r_fk, p.r_gk, p.r_rk};
-    FastPar<R> fp; fp.Td = Tt; fp.Hz = p.Hz; fp.Sz = p.Sz; fp.z = p.z;
+    FastPar<R> fp; fp.Hz = p.Hz; fp.Sz = p.Sz; fp.z = p.z;
     fp.c_sk = 1.0 - p.r_sk; fp.c_fk = 1.0 - p.r_fk; fp.c_gk = 1.0 - p.r_gk; fp.c_rk = 1.0 - p.r_rk;
     const double to_mm = 1e3 / area;
     double v[12];
@@ -56,7 +56,7 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
         for (long i = 0; i < n; ++i) {
             if (mode == 0) smart_step<R, true, false>(s, p, rain[i], peva[i], o);
             else if (mode == 1) smart_step<R, false, false>(s, p, rain[i], peva[i], o);
-            else smart_step_fast<R, 1>(s, fp, kc, carry, __dsub_rn(__dmul_rn(rain[i], fp.Td), peva[i]), o);
+            else smart_step_fast<R, 1>(s, fp, kc, carry, __dsub_rn(__dmul_rn(rain[i], Tt), peva[i]), o);
             acc += o.q_riv; agw += o.q_gw; aall += o.q_all;
             if (--countdown == 0) {
                 countdown = gap;
