@@ -69,12 +69,16 @@ typedef struct smart_batch_desc {
     int32_t report_gap;             /* simulation steps per reporting step (structure.py:75) */
     int32_t report_type;            /* SMART_REPORT_SUMMARY | SMART_REPORT_RAW */
     uint32_t flags;                 /* SMART_FLAG_* */
-    int32_t reserved0;
+    int32_t forcing_repeat;         /* 0 or 1: rain/peva hold one row per step.  k > 1: one row per block
+                                       of k steps with constant forcing (what the reference's daily ->
+                                       hourly split produces, timeframe.py:167-186), values already per
+                                       STEP (daily total / k); rows = n_steps / k.  Needs report_gap == k,
+                                       SMART_REPORT_SUMMARY, n_steps % k == n_warmup % k == 0, FP64 entry. */
     double dt_sec;                  /* simulation time step in seconds */
 
     /* ---- inputs */
     const double *params;           /* [N][10] row-major, always binary64 */
-    const double *rain;             /* [T][C]  mm per step  (C == 1: plain [T]) */
+    const double *rain;             /* [T][C]  mm per step  (C == 1: plain [T]); [T / forcing_repeat][C] */
     const double *peva;             /* [T][C]  mm per step */
     const double *area_m2;          /* [C] */
     const double *obs;              /* [n_report][C], NaN = missing; NULL = no scoring */
@@ -128,6 +132,11 @@ int smart_batch_run_f32(const smart_batch_desc *d, void *stream);
  */
 int smart_disaggregate(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double *out,
                        void *stream);
+/* Same stamping without the division: out[(i * repeat + k)][c] = in[i][c]. */
+int smart_expand(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double *out, void *stream);
+/* The general form: out[(i * repeat + k)][c] = in[i][c] / divisor (one IEEE division per value). */
+int smart_stamp(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double divisor, double *out,
+                void *stream);
 
 /*
  * Objective functions of already simulated series (montecarlo.py:193-209 on its own):

@@ -32,7 +32,7 @@ FLAG_NO_TMA = 0x2
 SYMBOLS = (
     "smart_version", "smart_last_error", "smart_batch_n_report", "smart_batch_workspace_bytes",
     "smart_obs_stats", "smart_batch_run_f64", "smart_batch_run_f32", "smart_score_discharge",
-    "smart_disaggregate", "smart_batch_run_host",
+    "smart_disaggregate", "smart_expand", "smart_stamp", "smart_batch_run_host",
     "smart_allsteps_host", "smart_fma_peak_probe",
 )
 
@@ -48,7 +48,7 @@ class BatchDesc(ctypes.Structure):
         ("report_gap", ctypes.c_int32),
         ("report_type", ctypes.c_int32),
         ("flags", ctypes.c_uint32),
-        ("reserved0", ctypes.c_int32),
+        ("forcing_repeat", ctypes.c_int32),
         ("dt_sec", ctypes.c_double),
         ("params", ctypes.c_void_p),
         ("rain", ctypes.c_void_p),
@@ -116,6 +116,11 @@ def load():
     lib.smart_disaggregate.restype = ctypes.c_int
     lib.smart_disaggregate.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32,
                                        ctypes.c_void_p, ctypes.c_void_p]
+    lib.smart_expand.restype = ctypes.c_int
+    lib.smart_expand.argtypes = lib.smart_disaggregate.argtypes
+    lib.smart_stamp.restype = ctypes.c_int
+    lib.smart_stamp.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                                ctypes.c_void_p, ctypes.c_void_p]
     lib.smart_batch_run_host.restype = ctypes.c_int
     lib.smart_batch_run_host.argtypes = [pdesc, ctypes.c_int, ctypes.c_int]
     lib.smart_allsteps_host.restype = ctypes.c_int

@@ -29,7 +29,7 @@ using namespace smart;
 
 constexpr int kChunkSingle = 512;  // forcing steps per smem stage, single catchment
 constexpr int kAccSlots = 8;       // per-thread binary64 accumulators parked in smem
-constexpr int kConstSlots = 8;     // per-thread R-typed constants of the fast step parked in smem (7 used)
+constexpr int kConstSlots = 14;    // per-thread R-typed constants of the fast step parked in smem
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
 #ifndef SMART_FAST_REGS_F64
 #define SMART_FAST_REGS_F64 96     // register budget of the fast FP64 kernel (sweep 80..104 in profiles/): 20 warps per SM, no spills
@@ -66,6 +66,7 @@ struct KArgs {
     int C, mpc, gap, report_type;
     int chunk, kc, use_tma, force_general;
     int has_extra, best_col, best_sign, first_report;
+    int rep, pad0;               // steps per forcing row (1 = one row per step)
     double dt, aar_ro, split[5], gw_constraint;
 };
 
@@ -160,12 +161,17 @@ struct Smem {
 };
 
 // ------------------------------------------------------------------ the time loop
-template <typename R, int kVariant, int BLOCK, bool kSingle>
+// kDaily: the forcing arrays hold one row per block of a.rep steps (constant forcing inside the
+// block, the reference's daily -> hourly disaggregation) and a.rep == a.gap, 'summary', warm-up a
+// whole number of blocks: one row = one reporting step, and the binary64 fast form advances a
+// whole block at a time (smart_block_fast).
+template <typename R, int kVariant, int BLOCK, bool kSingle, bool kDaily>
 __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
                                              const FastPar<R> &fp_, const Smem<R, BLOCK> &sm, long long m, bool active,
                                              int c, int col, int c_base, double area, double &gw_out, StepOut<R> &o)
 {
     constexpr bool kFast = kVariant == kVariantFast;
+    constexpr bool kWide = sizeof(R) == 8;    // binary64 state: run-long sums stay in registers
     const int kc = kSingle ? 1 : a.kc;
     const int tile = stage_doubles(a.chunk, kc);
     const int tid = threadIdx.x;
@@ -178,21 +184,23 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     double &RIV0 = sm.acc[6 * BLOCK + tid];   // river store at the start of the main run
     double &SCALE = sm.acc[7 * BLOCK + tid];  // mm per step -> m3/s (and / report_gap for 'summary')
     const R *kconst = sm.kconst + tid;
-    constexpr bool kWide = sizeof(R) == 8;    // binary64 state: run-long sums stay in registers
 
+    // rows of the forcing arrays: one per step, or one per block of a.rep steps
+    const int rep = kDaily ? a.rep : 1;
+    const long long rowsW = a.W / rep, rowsT = a.T / rep;
     const int chunk = a.chunk;
-    const int nWc = static_cast<int>((a.W + chunk - 1) / chunk);
-    const int nTot = nWc + static_cast<int>((a.T + chunk - 1) / chunk);
+    const int nWc = static_cast<int>((rowsW + chunk - 1) / chunk);
+    const int nTot = nWc + static_cast<int>((rowsT + chunk - 1) / chunk);
     // with one simulation step per reporting step 'raw' and 'summary' coincide (structure.py:190-195)
-    const bool summary = a.report_type == SMART_REPORT_SUMMARY || a.gap == 1;
+    const bool summary = kDaily || a.report_type == SMART_REPORT_SUMMARY || a.gap == 1;
 
     auto chunk_span = [&](int ci, long long &t0, int &n) {
         if (ci < nWc) {
             t0 = static_cast<long long>(ci) * chunk;
-            n = static_cast<int>(min(static_cast<long long>(chunk), a.W - t0));
+            n = static_cast<int>(min(static_cast<long long>(chunk), rowsW - t0));
         } else {
             t0 = static_cast<long long>(ci - nWc) * chunk;
-            n = static_cast<int>(min(static_cast<long long>(chunk), a.T - t0));
+            n = static_cast<int>(min(static_cast<long long>(chunk), rowsT - t0));
         }
     };
     // TMA producer (one thread): even element counts go through cp.async.bulk (16-byte
@@ -214,8 +222,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
             tma_bulk_g2s(dp, a.peva + t0, n_even * 8u, &sm.full[b]);
         }
     };
-
-    // generic producer (every thread): rows t0..t0+n, columns c_base..c_base+kc of [T][C], as
+    // generic producer (every thread): rows t0..t0+n, columns c_base..c_base+kc of [rows][C], as
     // asynchronous copies so that the next stage loads while the current one is consumed
     auto async_issue = [&](int ci) {
         long long t0;
@@ -245,6 +252,31 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     carry.valid = false;
     o.q_riv = o.q_gw = o.q_all = R(0);
     o.aeva = o.q_ove = o.q_dra = o.q_int = o.q_sgw = o.q_dgw = R(0);
+
+    // one reporting step (structure.py:188-195 + montecarlo.py:193-203), sval in m3/s
+    auto report = [&](R sval) {
+        if (!kWide) {   // binary32 state: fold the per-gap sums into binary64
+            GN += static_cast<double>(agw);
+            GD += static_cast<double>(aall);
+            agw = aall = R(0);
+        }
+        if (a.discharge != nullptr && active)
+            static_cast<R *>(a.discharge)[static_cast<long long>(r) * a.ld_q + m] = sval;
+        if (a.obs != nullptr) {
+            const double e = __ldg(&a.obs[static_cast<long long>(r) * a.C + c]);
+            if (e == e) {                            // montecarlo.py:195-196 NaN mask
+                const double ebar = a.obs_stats[c * SMART_OBS_STATS + 2];
+                const double ds = static_cast<double>(sval) - ebar;
+                const double de = e - ebar;
+                const double df = ds - de;
+                A += ds;
+                B = fma(ds, ds, B);
+                Cc = fma(ds, de, Cc);
+                E = fma(df, df, E);
+            }
+        }
+        ++r;
+    };
 
     if (a.use_tma) {
         if (tid == 0) tma_issue(0);
@@ -279,61 +311,69 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         }
         const double *fr = sm.rain + b * tile + col;
         const double *fp = sm.peva + b * tile + col;
-        // wet/dry driver of the fast step, formed one step ahead of the state
-        // (T sits in shared memory next to the other early-fetch constants; binary64 in both modes)
-        const double *tdp = sm.td + tid;
-        double ex_next = kFast ? __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]) : 0.0;
-        for (int i = 0; i < n; ++i) {
-            if (kFast) {
-                const double ex_d = ex_next;
-                fr += kc;
-                fp += kc;
-                ex_next = __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]);   // last step of a stage: padding row, unused
-                smart_step_fast<R, BLOCK>(s, fp_, kconst, carry, ex_d, o);
-            } else {
-                smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
-                fr += kc;
-                fp += kc;
-            }
-            acc += o.q_riv;
-            // groundwater share (structure.py:191, :194-195): 'summary' sums every step, 'raw' only
-            // the sampled ones.  Fast form: the pathway total is recovered from the river's mass
-            // balance (sum q_in = sum q_out + dV_river), so only sum q_out is accumulated.
-            if (summary) {
-                agw += o.q_gw;
-                if (!kFast) aall += o.q_all;
-            }
-            if (--countdown == 0) {
-                countdown = a.gap;
-                const R sval = (summary ? acc : o.q_riv) * static_cast<R>(SCALE);   // structure.py:190 | :193
-                if (summary) {
-                    if (kFast) GD += static_cast<double>(acc);   // once per report step: lives in shared memory
+        const double *tdp = sm.td + tid;      // T in binary64 (both modes), parked in shared memory
+        if (kDaily) {
+            const bool in_main = ci >= nWc;
+            for (int i = 0; i < n; ++i) {
+                const double ex_d = __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]);   // structure.py:353-355
+                if constexpr (kFast && kWide) {
+                    smart_block_fast<BLOCK>(s, fp_, kconst, carry, ex_d, rep, acc, agw);
                 } else {
-                    agw += o.q_gw;
-                    aall += o.q_all;
-                }
-                acc = R(0);
-                if (!kWide) {   // binary32 state: fold the per-gap sums into binary64
-                    GN += static_cast<double>(agw);
-                    GD += static_cast<double>(aall);
-                    agw = aall = R(0);
-                }
-                if (a.discharge != nullptr && active)
-                    static_cast<R *>(a.discharge)[static_cast<long long>(r) * a.ld_q + m] = sval;
-                if (a.obs != nullptr) {
-                    const double e = __ldg(&a.obs[static_cast<long long>(r) * a.C + c]);
-                    if (e == e) {                            // montecarlo.py:195-196 NaN mask
-                        const double ebar = a.obs_stats[c * SMART_OBS_STATS + 2];
-                        const double ds = static_cast<double>(sval) - ebar;
-                        const double de = e - ebar;
-                        const double df = ds - de;
-                        A += ds;
-                        B = fma(ds, ds, B);
-                        Cc = fma(ds, de, Cc);
-                        E = fma(df, df, E);
+                    for (int h = 0; h < rep; ++h) {
+                        if (kFast) {
+                            smart_step_fast<R, BLOCK>(s, fp_, kconst, carry, ex_d, o);
+                        } else {
+                            smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
+                            aall += o.q_all;
+                        }
+                        acc += o.q_riv;
+                        agw += o.q_gw;
                     }
                 }
-                ++r;
+                fr += kc;
+                fp += kc;
+                if (in_main) {
+                    const R sval = acc * static_cast<R>(SCALE);
+                    if (kFast) GD += static_cast<double>(acc);
+                    acc = R(0);
+                    report(sval);
+                }
+            }
+        } else {
+            // wet/dry driver of the fast step, formed one step ahead of the state
+            double ex_next = kFast ? __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]) : 0.0;
+            for (int i = 0; i < n; ++i) {
+                if (kFast) {
+                    const double ex_d = ex_next;
+                    fr += kc;
+                    fp += kc;
+                    ex_next = __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]);   // last step of a stage: padding row, unused
+                    smart_step_fast<R, BLOCK>(s, fp_, kconst, carry, ex_d, o);
+                } else {
+                    smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
+                    fr += kc;
+                    fp += kc;
+                }
+                acc += o.q_riv;
+                // groundwater share (structure.py:191, :194-195): 'summary' sums every step, 'raw'
+                // only the sampled ones.  Fast form: the pathway total is recovered from the river's
+                // mass balance (sum q_in = sum q_out + dV_river), so only sum q_out is accumulated.
+                if (summary) {
+                    agw += o.q_gw;
+                    if (!kFast) aall += o.q_all;
+                }
+                if (--countdown == 0) {
+                    countdown = a.gap;
+                    const R sval = (summary ? acc : o.q_riv) * static_cast<R>(SCALE);   // structure.py:190 | :193
+                    if (summary) {
+                        if (kFast) GD += static_cast<double>(acc);   // once per report step: shared memory
+                    } else {
+                        agw += o.q_gw;
+                        aall += o.q_all;
+                    }
+                    acc = R(0);
+                    report(sval);
+                }
             }
         }
         __syncthreads();   // every thread is done with stage b before it is refilled
@@ -363,7 +403,7 @@ __device__ __forceinline__ void finish_scores(const double *st, double A, double
     sc[6] = sqrt(E / n);                                      // RMSE
 }
 
-template <typename R, int kVariant, int BLOCK, bool kSingle>
+template <typename R, int kVariant, int BLOCK, bool kSingle, bool kDaily>
 __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
                                            long long m, bool active, int c, int col, int c_base, double area)
 {
@@ -403,8 +443,27 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         kconst[4 * BLOCK] = p.r_fk;
         kconst[5 * BLOCK] = p.r_gk;
         kconst[6 * BLOCK] = p.r_rk;
-        sm.td[tid] = T;
+        if (kDaily && sizeof(R) == 8) {
+            // closed form of a dry block of a.rep steps (smart_block_fast): c_x^rep and
+            // K_x = r_x * sum_{h<rep} c_w^(rep-1-h) c_x^h by Horner, no cancellation
+            const double cx[3] = {1.0 - r_sk, 1.0 - r_fk, 1.0 - r_gk}, rx[3] = {r_sk, r_fk, r_gk};
+            const double cw = 1.0 - r_rk;
+            double pw_w = 1.0;
+            for (int h = 0; h < a.rep; ++h) pw_w *= cw;
+            kconst[10 * BLOCK] = static_cast<R>(pw_w);
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {
+                double G = 0.0, pxh = 1.0;
+                for (int h = 0; h < a.rep; ++h) {
+                    G = fma(cw, G, pxh);
+                    pxh *= cx[x];
+                }
+                kconst[(7 + x) * BLOCK] = static_cast<R>(pxh);
+                kconst[(11 + x) * BLOCK] = static_cast<R>(rx[x] * G);
+            }
+        }
     }
+    sm.td[tid] = T;
 
     // initial conditions in m3 exactly as the reference writes them, then to mm
     const double to_mm = 1e3 / area;
@@ -438,7 +497,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 
     double gw = 0.0;
     StepOut<R> o;
-    run_timeline<R, kVariant, BLOCK, kSingle>(a, s, p, fp_, sm, m, active, c, col, c_base, area, gw, o);
+    run_timeline<R, kVariant, BLOCK, kSingle, kDaily>(a, s, p, fp_, sm, m, active, c, col, c_base, area, gw, o);
 
     // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
     double target = -CUDART_INF;
@@ -525,7 +584,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 // all of its members qualify for the merged form and runs in exactly one of the two launches;
 // in the other it exits at once.  Separate kernels keep the fast variant's register count
 // (and so its occupancy) independent of the branch-faithful code.
-template <typename R, int kVariant, int BLOCK, int MAX_REGS, bool kSingle>
+template <typename R, int kVariant, int BLOCK, int MAX_REGS, bool kSingle, bool kDaily>
 __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -566,7 +625,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         __syncthreads();
     }
 
-    run_member<R, kVariant, BLOCK, kSingle>(a, smem_raw, par, m, active, c, col, c_base, area);
+    run_member<R, kVariant, BLOCK, kSingle, kDaily>(a, smem_raw, par, m, active, c, col, c_base, area);
 }
 
 __global__ void best_finalize_kernel(const double *blk_score, const long long *blk_index, int n_blocks, int sign,
@@ -654,11 +713,10 @@ __global__ void obs_stats_kernel(const double *obs, long long n_report, int C, d
     }
 }
 
-// out[(i * repeat + k) * C + c] = in[i * C + c] / repeat   (timeframe.py:180-183)
-__global__ void disaggregate_kernel(const double *in, long long n_in, int C, int repeat, double *out)
+// out[(i * repeat + k) * C + c] = in[i * C + c] / div   (timeframe.py:180-183; div = repeat or 1)
+__global__ void disaggregate_kernel(const double *in, long long n_in, int C, int repeat, double div, double *out)
 {
     const long long total = n_in * repeat * C;
-    const double div = static_cast<double>(repeat);
     for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < total;
          j += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long row = j / C;
@@ -766,6 +824,15 @@ int validate(const smart_batch_desc *d, bool host_mode = false)
         if (!d->initial_state && d->n_warmup % d->report_gap != 0)
             return fail(SMART_ERR_GAP, "cannot reshape the warm-up run into (-1, report_gap)");
     }
+    if (d->forcing_repeat > 1) {
+        // block-constant forcing: only the configuration the reference's disaggregation produces
+        if (d->n_steps % d->forcing_repeat != 0 || d->n_warmup % d->forcing_repeat != 0 ||
+            d->report_gap != d->forcing_repeat || d->report_type != SMART_REPORT_SUMMARY || d->initial_state ||
+            d->last_state)
+            return fail(SMART_ERR_BAD_ARG,
+                        "forcing_repeat > 1 needs report_gap == forcing_repeat, 'summary' reporting, run and warm-up "
+                        "lengths that are multiples of it, and no initial_state/last_state");
+    }
     if (d->discharge && d->ld_discharge < d->n_members)
         return fail(SMART_ERR_BAD_ARG, "ld_discharge must be >= n_members");
     if (d->best_sign != 0) {
@@ -817,9 +884,13 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
 
     const int block = block_of(d);
     const int blocks = n_blocks_of(d, block);
+    const bool daily = d->forcing_repeat > 1;
+    if (daily && sizeof(R) != 8)
+        return fail(SMART_ERR_BAD_ARG, "forcing_repeat > 1 is implemented for the FP64 entry point only");
+    a.rep = daily ? d->forcing_repeat : 1;
     if (a.C == 1) {
         a.kc = 1;
-        a.chunk = block == kBlockLarge ? kChunkSingle : kChunkSingle / 2;
+        a.chunk = daily ? 64 : (block == kBlockLarge ? kChunkSingle : kChunkSingle / 2);
         const bool aligned = (reinterpret_cast<uintptr_t>(d->rain) % 16 == 0) &&
                              (reinterpret_cast<uintptr_t>(d->peva) % 16 == 0);
         a.use_tma = (aligned && !(d->flags & SMART_FLAG_NO_TMA)) ? 1 : 0;
@@ -827,7 +898,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.kc = (block - 1) / a.mpc + 2;              // catchments one CTA can straddle
         if (a.kc > a.C) a.kc = a.C;
         int chunk = (block == kBlockLarge ? 24 * 1024 : 12 * 1024) / (2 * 2 * 8 * a.kc);
-        chunk = chunk > 512 ? 512 : chunk;
+        chunk = chunk > (daily ? 64 : 512) ? (daily ? 64 : 512) : chunk;
         chunk &= ~7;
         if (chunk < 8) return fail(SMART_ERR_BAD_ARG, "members_per_catchment too small for one CTA tile");
         a.chunk = chunk;
@@ -852,20 +923,29 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     constexpr int kRoomyRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64 : SMART_FAST_REGS_F32;
     constexpr int kSlowRegs = 128;
     Kernel fast_lean, fast_roomy, general, fluxes;
-    auto pick = [&](auto block_tag, auto single_tag) {
+    auto pick = [&](auto block_tag, auto single_tag, auto daily_tag) {
         constexpr int B = decltype(block_tag)::value;
         constexpr bool S = decltype(single_tag)::value;
-        fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S>;
-        fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S>;
-        general = smart_batch_kernel<R, kVariantGeneral, B, kSlowRegs, S>;
-        fluxes = smart_batch_kernel<R, kVariantFluxes, B, kSlowRegs, S>;
+        constexpr bool D = decltype(daily_tag)::value && sizeof(R) == 8;
+        fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S, D>;
+        fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S, D>;
+        general = smart_batch_kernel<R, kVariantGeneral, B, kSlowRegs, S, D>;
+        fluxes = smart_batch_kernel<R, kVariantFluxes, B, kSlowRegs, S, false>;
     };
     using BL = std::integral_constant<int, kBlockLarge>;
     using BS = std::integral_constant<int, kBlockSmall>;
-    if (block == kBlockLarge) {
-        if (a.C == 1) pick(BL{}, std::true_type{}); else pick(BL{}, std::false_type{});
-    } else {
-        if (a.C == 1) pick(BS{}, std::true_type{}); else pick(BS{}, std::false_type{});
+    using Yes = std::true_type;
+    using No = std::false_type;
+    const int sel = (block == kBlockLarge ? 4 : 0) | (a.C == 1 ? 2 : 0) | (daily ? 1 : 0);
+    switch (sel) {
+        case 0: pick(BS{}, No{}, No{}); break;
+        case 1: pick(BS{}, No{}, Yes{}); break;
+        case 2: pick(BS{}, Yes{}, No{}); break;
+        case 3: pick(BS{}, Yes{}, Yes{}); break;
+        case 4: pick(BL{}, No{}, No{}); break;
+        case 5: pick(BL{}, No{}, Yes{}); break;
+        case 6: pick(BL{}, Yes{}, No{}); break;
+        default: pick(BL{}, Yes{}, Yes{}); break;
     }
     if (d->last_state) {
         if ((rc = go(fluxes))) return rc;
@@ -946,18 +1026,36 @@ int smart_batch_run_f32(const smart_batch_desc *d, void *stream)
     return launch<float>(d, static_cast<cudaStream_t>(stream));
 }
 
-int smart_disaggregate(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double *out,
-                       void *stream)
+static int stamp_rows(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double div, double *out,
+                      void *stream)
 {
     if (!in || !out || n_in < 1 || n_catchments < 1 || repeat < 1)
-        return fail(SMART_ERR_BAD_ARG, "smart_disaggregate: bad argument");
+        return fail(SMART_ERR_BAD_ARG, "smart_disaggregate / smart_expand: bad argument");
     const long long total = static_cast<long long>(n_in) * repeat * n_catchments;
     const int threads = 256;
     const long long want = (total + threads - 1) / threads;
     const int blocks = static_cast<int>(want < 148 * 16 ? want : 148 * 16);
-    disaggregate_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, n_in, n_catchments, repeat, out);
+    disaggregate_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, n_in, n_catchments, repeat, div,
+                                                                                   out);
     SMART_CUDA(cudaGetLastError());
     return SMART_OK;
+}
+
+int smart_disaggregate(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double *out,
+                       void *stream)
+{
+    return stamp_rows(in, n_in, n_catchments, repeat, static_cast<double>(repeat), out, stream);
+}
+
+int smart_expand(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double *out, void *stream)
+{
+    return stamp_rows(in, n_in, n_catchments, repeat, 1.0, out, stream);
+}
+
+int smart_stamp(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double divisor, double *out,
+                void *stream)
+{
+    return stamp_rows(in, n_in, n_catchments, repeat, divisor, out, stream);
 }
 
 int smart_score_discharge(const void *discharge, int64_t ld_discharge, int64_t n_members, int64_t n_report,

@@ -240,14 +240,121 @@ __device__ __forceinline__ R soil_total(const MemberState<R> &s)
 __device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
 __device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >= 0; }
 
-// ex_d = rain * T - peva (structure.py:353-355, two separately rounded binary64 operations) is
-// formed by the caller one step ahead: it depends on the forcing only, which takes the
-// shared-memory load and two FP64 latencies off the head of every step.
+// ---- pieces of the fast step ---------------------------------------------------------------
+
+// Wet hour, soil part (structure.py:360-399): overland split, fill ladder, saturation excess,
+// three leak passes.  ex = rain * T - peva >= 0.  Returns the three merged inflows.
+template <typename R, int kStride>
+__device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R> &p, const R *kc,
+                                              FastCarry<R> &carry, R ex, R &in_quick, R &in_int, R &in_gw)
+{
+    constexpr bool kLeakByDifference = sizeof(R) == 8;
+    const R zero = R(0);
+    R tot = carry.tot;
+    if (!carry.valid) tot = soil_total(s);
+    in_quick = (p.Hz * tot) * ex;                   // :363-364
+    const R u0 = in_quick - ex;                     // u = -(excess rain still to place) <= 0
+    R u = u0;
+    auto fill = [&](int i) {                        // :367-374
+        const R w = s.ly[i] - u;                    // level if the layer took everything
+        const R t = p.z - w;
+        const bool fits = sign_clear(t);
+        s.ly[i] = fits ? w : p.z;
+        u = fits ? zero : t;
+        return fits;
+    };
+#ifndef SMART_NO_EARLY_OUT
+    // most often the first layer takes everything for every member of the warp
+    const bool done = fill(0);
+    if (__any_sync(__activemask(), !done)) {
+        fill(1); fill(2); fill(3); fill(4); fill(5);
+    }
+#else
+    fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
+#endif
+    in_quick = fma(kc[1 * kStride], -u, in_quick);  // + D * saturation excess (:376)
+    in_int = kc[2 * kStride] * (-u);                // (1 - D) * saturation excess (:377)
+    const R sp = p.Sz * tot;                        // :379
+    R pw[6];
+    pw[0] = sp;
+    pw[1] = sp * sp;
+    pw[2] = pw[1] * sp;
+    pw[3] = pw[1] * pw[1];
+    pw[4] = pw[3] * sp;
+    pw[5] = pw[2] * pw[2];
+    if (kLeakByDifference) {
+        // soil total after the fill, summed like tot1/tot3 so that a zero leak gives exactly 0
+        const R tot_f = soil_total(s);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s.ly[i] = fma(-s.ly[i], pw[i], s.ly[i]);            // :381-385
+        const R tot1 = soil_total(s);
+        in_int += tot_f - tot1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {                                                   // :388-399
+            const R f2 = i == 0 ? sp : sp * inv_const<R>(i);
+            s.ly[i] = fma(-s.ly[i], f2, s.ly[i]);
+        }
+#pragma unroll
+        for (int i = 5; i >= 0; --i) s.ly[i] = fma(-s.ly[i], pw[5 - i], s.ly[i]);
+        const R tot3 = soil_total(s);
+        in_gw = tot1 - tot3;
+        carry.tot = tot3;
+        carry.valid = true;
+    } else {
+        in_gw = zero;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const R leak = s.ly[i] * pw[i];
+            in_int += leak;
+            s.ly[i] -= leak;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const R leak = s.ly[i] * (i == 0 ? sp : sp * inv_const<R>(i));
+            in_gw += leak;
+            s.ly[i] -= leak;
+        }
+#pragma unroll
+        for (int i = 5; i >= 0; --i) {
+            const R leak = s.ly[i] * pw[5 - i];
+            in_gw += leak;
+            s.ly[i] -= leak;
+        }
+        carry.valid = false;
+    }
+}
+
+// Dry hour, soil part (structure.py:407-419): the deficit d = peva - rain * T > 0 is taken from
+// the layers top down, decayed by C each time a layer runs empty.
+template <typename R>
+__device__ __forceinline__ void fast_dry_soil(MemberState<R> &s, R C, R d)
+{
+    const R zero = R(0);
+    auto take = [&](int i) {
+        const R t = s.ly[i] - d;
+        const bool enough = sign_clear(t);          // level >= deficit
+        s.ly[i] = enough ? t : zero;
+        d = enough ? zero : C * (-t);
+        return enough;
+    };
+#ifndef SMART_NO_EARLY_OUT
+    const bool done = take(0);
+    if (__any_sync(__activemask(), !done)) {
+        take(1); take(2); take(3); take(4); take(5);
+    }
+#else
+    take(0); take(1); take(2); take(3); take(4); take(5);
+#endif
+}
+
+// One hour of the fast step.  ex_d = rain * T - peva (structure.py:353-355, two separately
+// rounded binary64 operations) is formed by the caller one step ahead: it depends on the
+// forcing only, which takes the shared-memory load and two FP64 latencies off the head of
+// every step.
 template <typename R, int kStride>
 __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar<R> &p, const R *kc,
                                                 FastCarry<R> &carry, double ex_d, StepOut<R> &o)
 {
-    constexpr bool kLeakByDifference = sizeof(R) == 8;
     constexpr bool kOneFma = sizeof(R) == 8;
     const R zero = R(0);
     R in_quick = zero, in_int = zero, in_gw = zero;
@@ -265,96 +372,9 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
     o.q_riv = q;
 
     if (ex_d >= 0.0) {
-        R tot = carry.tot;
-        if (!carry.valid) tot = soil_total(s);
-        const R ex = static_cast<R>(ex_d);
-        in_quick = (p.Hz * tot) * ex;                   // :363-364
-        const R u0 = in_quick - ex;                     // u = -(excess rain still to place) <= 0
-        R u = u0;
-        auto fill = [&](int i) {                        // :367-374
-            const R w = s.ly[i] - u;                    // level if the layer took everything
-            const R t = p.z - w;
-            const bool fits = sign_clear(t);
-            s.ly[i] = fits ? w : p.z;
-            u = fits ? zero : t;
-            return fits;
-        };
-#ifndef SMART_NO_EARLY_OUT
-        // most often the first layer takes everything for every member of the warp
-        const bool done = fill(0);
-        if (__any_sync(__activemask(), !done)) {
-            fill(1); fill(2); fill(3); fill(4); fill(5);
-        }
-#else
-        fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
-#endif
-        in_quick = fma(kc[1 * kStride], -u, in_quick);  // + D * saturation excess (:376)
-        in_int = kc[2 * kStride] * (-u);                // (1 - D) * saturation excess (:377)
-        const R sp = p.Sz * tot;                        // :379
-        R pw[6];
-        pw[0] = sp;
-        pw[1] = sp * sp;
-        pw[2] = pw[1] * sp;
-        pw[3] = pw[1] * pw[1];
-        pw[4] = pw[3] * sp;
-        pw[5] = pw[2] * pw[2];
-        if (kLeakByDifference) {
-            // soil total after the fill, summed like tot1/tot3 so that a zero leak gives exactly 0
-            const R tot_f = soil_total(s);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) s.ly[i] = fma(-s.ly[i], pw[i], s.ly[i]);            // :381-385
-            const R tot1 = soil_total(s);
-            in_int += tot_f - tot1;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {                                                   // :388-399
-                const R f2 = i == 0 ? sp : sp * inv_const<R>(i);
-                s.ly[i] = fma(-s.ly[i], f2, s.ly[i]);
-            }
-#pragma unroll
-            for (int i = 5; i >= 0; --i) s.ly[i] = fma(-s.ly[i], pw[5 - i], s.ly[i]);
-            const R tot3 = soil_total(s);
-            in_gw = tot1 - tot3;
-            carry.tot = tot3;
-            carry.valid = true;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const R leak = s.ly[i] * pw[i];
-                in_int += leak;
-                s.ly[i] -= leak;
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const R leak = s.ly[i] * (i == 0 ? sp : sp * inv_const<R>(i));
-                in_gw += leak;
-                s.ly[i] -= leak;
-            }
-#pragma unroll
-            for (int i = 5; i >= 0; --i) {
-                const R leak = s.ly[i] * pw[5 - i];
-                in_gw += leak;
-                s.ly[i] -= leak;
-            }
-            carry.valid = false;
-        }
+        fast_wet_soil<R, kStride>(s, p, kc, carry, static_cast<R>(ex_d), in_quick, in_int, in_gw);
     } else {
-        R d = static_cast<R>(-ex_d);                    // :407-419
-        const R C = kc[0];
-        auto take = [&](int i) {
-            const R t = s.ly[i] - d;
-            const bool enough = sign_clear(t);          // level >= deficit
-            s.ly[i] = enough ? t : zero;
-            d = enough ? zero : C * (-t);
-            return enough;
-        };
-#ifndef SMART_NO_EARLY_OUT
-        const bool done = take(0);
-        if (__any_sync(__activemask(), !done)) {
-            take(1); take(2); take(3); take(4); take(5);
-        }
-#else
-        take(0); take(1); take(2); take(3); take(4); take(5);
-#endif
+        fast_dry_soil<R>(s, kc[0], static_cast<R>(-ex_d));
         carry.valid = false;
     }
 
@@ -364,6 +384,66 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
     s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - q_quick) + in_quick;
     s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - q_int) + in_int;
     s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
+}
+
+// ---- a whole block of `rep` steps under constant forcing (binary64 only) --------------------
+// The reference's own daily -> hourly disaggregation (timeframe.py:167-186) gives every hour of
+// a day the same rain and PET, so the wet/dry predicate holds for the whole block.
+//  * wet block: `rep` hourly steps as above (the soil is nonlinear in its own state);
+//  * dry block: the stores receive nothing for `rep` steps, so they, the river and the two
+//    running sums evolve LINEARLY and are advanced in closed form:
+//        V_x(rep) = c_x^rep V_x,    W(rep) = c_w^rep W + sum_x K_x V_x,
+//        K_x = r_x * sum_{h<rep} c_w^(rep-1-h) c_x^h   (Horner sum at set-up, no cancellation),
+//    and what left each store gives the sums by mass balance: sum Q_gw = G - G(rep),
+//    sum Q_out = (W - W(rep)) + sum_x (V_x - V_x(rep)).  Only the soil ladder is walked hour by
+//    hour, or in one subtraction when every member's top layer covers the block's demand.
+// kc slots 7..13: c_sk^rep, c_fk^rep, c_gk^rep, c_rk^rep, K_sk, K_fk, K_gk.
+// acc += sum of river outflow over the block, agw += sum of groundwater outflow (mm).
+template <int kStride>
+__device__ __forceinline__ void smart_block_fast(MemberState<double> &s, const FastPar<double> &p, const double *kc,
+                                                 FastCarry<double> &carry, double ex_d, int rep, double &acc,
+                                                 double &agw)
+{
+    if (ex_d >= 0.0) {
+        for (int h = 0; h < rep; ++h) {
+            const double q_quick = s.ove * kc[3 * kStride];
+            const double q_int = s.itf * kc[4 * kStride];
+            const double q_gw = s.sgw * kc[5 * kStride];
+            const double q = s.riv * kc[6 * kStride];
+            const double q_in = (q_quick + q_int) + q_gw;
+            s.riv = fma(s.riv, p.c_rk, q_in);
+            acc += q;
+            agw += q_gw;
+            double in_quick, in_int, in_gw;
+            fast_wet_soil<double, kStride>(s, p, kc, carry, ex_d, in_quick, in_int, in_gw);
+            s.ove = fma(s.ove, p.c_sk, in_quick);
+            s.itf = fma(s.itf, p.c_fk, in_int);
+            s.sgw = fma(s.sgw, p.c_gk, in_gw);
+        }
+    } else {
+        const double d0 = -ex_d;
+        // per member: if the top layer alone meets the whole block's demand the block is one
+        // subtraction, else the ladder is walked step by step (a member's arithmetic never
+        // depends on what the other lanes of its warp do)
+        const double left = s.ly[0] - d0 * static_cast<double>(rep);
+        if (sign_clear(left)) {
+            s.ly[0] = left;
+        } else {
+            const double C = kc[0];
+            for (int h = 0; h < rep; ++h) fast_dry_soil<double>(s, C, d0);
+        }
+        carry.valid = false;
+        const double a = s.ove, b = s.itf, g = s.sgw, w = s.riv;
+        const double a_n = a * kc[7 * kStride], b_n = b * kc[8 * kStride], g_n = g * kc[9 * kStride];
+        const double w_n = fma(kc[11 * kStride], a, fma(kc[12 * kStride], b, fma(kc[13 * kStride], g, w * kc[10 * kStride])));
+        const double out_g = g - g_n;
+        agw += out_g;
+        acc += ((w - w_n) + (a - a_n)) + ((b - b_n) + out_g);
+        s.ove = a_n;
+        s.itf = b_n;
+        s.sgw = g_n;
+        s.riv = w_n;
+    }
 }
 
 }  // namespace smart

@@ -18,6 +18,9 @@ from . import _native
 
 SCORE_NAMES = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
 
+# engine-level flag (not passed to the library): always hand the kernel one forcing row per step
+FLAG_NO_BLOCK_MODE = 0x10000
+
 
 def _torch():
     import torch
@@ -72,14 +75,31 @@ class BatchEngine(object):
             raise ValueError("rain and peva must have the same shape")
         self.n_catchments = 1 if rain.dim() == 1 else int(rain.shape[1])
         self.members_per_catchment = int(members_per_catchment) if members_per_catchment else 0
-        self.rain = rain.to(self.device, torch.float64).contiguous()
-        self.peva = peva.to(self.device, torch.float64).contiguous()
-        # forcing_repeat > 1: rain/peva are totals over `forcing_repeat` simulation steps (e.g. daily
-        # values for an hourly model); the equal split of timeframe.py:167-186 happens on the device
-        if int(forcing_repeat) > 1:
-            self.rain = self._disaggregate(self.rain, int(forcing_repeat))
-            self.peva = self._disaggregate(self.peva, int(forcing_repeat))
-        self.n_steps = int(self.rain.shape[0])
+        rain = rain.to(self.device, torch.float64).contiguous()
+        peva = peva.to(self.device, torch.float64).contiguous()
+        # Block-constant forcing.  forcing_repeat = k > 1: rain/peva are totals over k simulation
+        # steps (e.g. daily values for an hourly model) and the equal split of
+        # timeframe.py:167-186 (value / k, one IEEE division) happens on the device.  Per-step
+        # series that are constant inside aligned blocks of report_gap steps -- what that split
+        # produces -- are detected and folded back to one row per block.  Either way the kernel
+        # then walks a dry block in closed form (smart_block_fast) when the run qualifies.
+        repeat = int(forcing_repeat)
+        gap = self.report_gap
+        if repeat > 1:
+            # (not `tensor / k`: torch multiplies by the reciprocal, which is not the reference's division)
+            rows_rain, rows_peva = self._stamp(rain, 1, float(repeat)), self._stamp(peva, 1, float(repeat))
+        else:
+            rows_rain, rows_peva = rain, peva
+            n = int(rain.shape[0])
+            if gap > 1 and n % gap == 0 and n >= gap:
+                br = rain.reshape((n // gap, gap) + tuple(rain.shape[1:]))
+                bp = peva.reshape((n // gap, gap) + tuple(peva.shape[1:]))
+                if bool((br == br[:, :1]).all()) and bool((bp == bp[:, :1]).all()):
+                    rows_rain, rows_peva, repeat = br[:, 0].contiguous(), bp[:, 0].contiguous(), gap
+        self._rows = (rows_rain, rows_peva)
+        self._repeat = repeat
+        self._hourly = None if repeat > 1 else (rows_rain, rows_peva)
+        self.n_steps = int(rows_rain.shape[0]) * repeat
         area = np.atleast_1d(np.asarray(area_m2, dtype=np.float64))
         if area.shape != (self.n_catchments,):
             raise ValueError("area_m2 must have one value per catchment")
@@ -105,15 +125,41 @@ class BatchEngine(object):
                                               torch.cuda.current_stream(self.device).cuda_stream)
             _native.check(rc)
 
-    def _disaggregate(self, coarse, repeat):
+    def _stamp(self, rows, repeat, divisor):
+        """out[i * repeat + k] = rows[i] / divisor on the device (smart_stamp): the equal split of
+        timeframe.py:180-183 with divisor = repeat, a plain expansion with divisor = 1."""
         torch = _torch()
-        shape = (coarse.shape[0] * repeat,) + tuple(coarse.shape[1:])
-        fine = torch.empty(shape, dtype=torch.float64, device=self.device)
+        shape = (rows.shape[0] * repeat,) + tuple(rows.shape[1:])
+        out = torch.empty(shape, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            rc = self.lib.smart_disaggregate(coarse.data_ptr(), coarse.shape[0], self.n_catchments, repeat,
-                                             fine.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+            rc = self.lib.smart_stamp(rows.data_ptr(), rows.shape[0], self.n_catchments, repeat, float(divisor),
+                                      out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
         _native.check(rc)
-        return fine
+        return out
+
+    def _expand(self, rows, repeat):
+        return self._stamp(rows, repeat, 1.0)
+
+    @property
+    def rain(self):
+        """Per-step rainfall on the device ([T] or [T, C])."""
+        return self._per_step()[0]
+
+    @property
+    def peva(self):
+        return self._per_step()[1]
+
+    def _per_step(self):
+        if self._hourly is None:
+            self._hourly = (self._expand(self._rows[0], self._repeat), self._expand(self._rows[1], self._repeat))
+        return self._hourly
+
+    def _block_mode(self, initial_state, last_state):
+        """Does this run qualify for one forcing row per reporting step (include/smart_b200.h)?"""
+        k = self._repeat
+        return (k > 1 and k == self.report_gap and self.report_type == _native.REPORT_SUMMARY and
+                self.precision == 'f64' and self.warm_up_steps % k == 0 and initial_state is None and
+                not last_state and not (self.flags & FLAG_NO_BLOCK_MODE))
 
     # ------------------------------------------------------------------ descriptor
     def _desc(self, n_members):
@@ -125,10 +171,8 @@ class BatchEngine(object):
         d.members_per_catchment = self.members_per_catchment if self.n_catchments > 1 else 1
         d.report_gap = self.report_gap
         d.report_type = self.report_type
-        d.flags = self.flags
+        d.flags = self.flags & 0xffff
         d.dt_sec = self.delta_sec
-        d.rain = self.rain.data_ptr()
-        d.peva = self.peva.data_ptr()
         d.area_m2 = self.area.data_ptr()
         if self.extra:   # truthiness, as structure.py:100
             d.has_extra = 1
@@ -169,6 +213,11 @@ class BatchEngine(object):
         n = int(p_dev.shape[0])
         d = self._desc(n)
         d.params = p_dev.data_ptr()
+        if self._block_mode(initial_state, last_state):
+            d.rain, d.peva = self._rows[0].data_ptr(), self._rows[1].data_ptr()
+            d.forcing_repeat = self._repeat
+        else:
+            d.rain, d.peva = self.rain.data_ptr(), self.peva.data_ptr()
         keep = [p_dev]
         res = {}
         out = out or {}

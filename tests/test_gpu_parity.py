@@ -75,7 +75,8 @@ def test_printed_known_answers(catchment):
 
 
 # ---------------------------------------------------------------- members: LHS sample, range corners, .lhs rows
-@pytest.mark.parametrize("flags", [0, 1, 2, 3])   # default, FORCE_GENERAL, NO_TMA, both
+# default (block mode: one forcing row per day), hourly fast path, FORCE_GENERAL, NO_TMA, combinations
+@pytest.mark.parametrize("flags", [0, 0x10000, 1, 2, 3, 0x10002, 0x10001])
 def test_members_match_reference_and_oracle_scores(catchment, flags):
     _torch()
     from oracle import scores as oscores
@@ -98,13 +99,29 @@ def test_members_match_reference_and_oracle_scores(catchment, flags):
     assert np.array_equal(sc[n0:, 7], file_scores[:, 7])
 
 
-def test_scores_only_equals_scores_with_discharge(catchment):
+@pytest.mark.parametrize("flags", [0, 0x10000])
+def test_scores_only_equals_scores_with_discharge(catchment, flags):
     _torch()
     g = load_golden("runs_members")
-    eng = make_engine(catchment, n_steps=24 * 400)
+    eng = make_engine(catchment, n_steps=24 * 400, flags=flags)
     a = eng.run(g["params"], discharge=True, scores=True)
     b = eng.run(g["params"], discharge=False, scores=True)
     assert np.array_equal(a["scores"].cpu().numpy(), b["scores"].cpu().numpy(), equal_nan=True)
+
+
+def test_block_mode_is_independent_of_batch_composition(catchment):
+    """A member's result must not depend on which other members share its warp (the warp-level
+    shortcuts of the fast path only skip work that would not change any value)."""
+    _torch()
+    g = load_golden("runs_members")
+    eng = make_engine(catchment, n_steps=24 * 600, obs=False)
+    full = eng.run(g["params"], discharge=True, scores=False)["discharge"].cpu().numpy()
+    rng = np.random.RandomState(0)
+    perm = rng.permutation(len(g["params"]))
+    shuffled = eng.run(g["params"][perm], discharge=True, scores=False)["discharge"].cpu().numpy()
+    assert np.array_equal(shuffled, full[:, perm])
+    alone = eng.run(g["params"][7:8], discharge=True, scores=False)["discharge"].cpu().numpy()
+    assert np.array_equal(alone[:, 0], full[:, 7])
 
 
 def test_best_member(catchment):

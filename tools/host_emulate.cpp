@@ -30,7 +30,19 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
     MemberPar<R> p;
     p.Td = Tt; p.C = C; p.D = D; p.omD = 1.0 - D; p.Hz = H / Z; p.Sz = S / Z; p.z = Z / 6.0;
     p.r_sk = dt / (SK * 3600.0); p.r_fk = dt / (FK * 3600.0); p.r_gk = dt / (GK * 3600.0); p.r_rk = dt / (RK * 3600.0);
-    R kc[7] = {C, D, 1.0 - D, p.r_sk, p.r_fk, p.r_gk, p.r_rk};
+    R kc[14] = {C, D, 1.0 - D, p.r_sk, p.r_fk, p.r_gk, p.r_rk};
+    {
+        const double cx[3] = {1.0 - p.r_sk, 1.0 - p.r_fk, 1.0 - p.r_gk}, rx[3] = {p.r_sk, p.r_fk, p.r_gk};
+        const double cw = 1.0 - p.r_rk;
+        double pw_w = 1.0;
+        for (int h = 0; h < gap; ++h) pw_w *= cw;
+        kc[10] = pw_w;
+        for (int x = 0; x < 3; ++x) {
+            double G = 0.0, pxh = 1.0;
+            for (int h = 0; h < gap; ++h) { G = fma(cw, G, pxh); pxh *= cx[x]; }
+            kc[7 + x] = pxh; kc[11 + x] = rx[x] * G;
+        }
+    }
     FastPar<R> fp; fp.Hz = p.Hz; fp.Sz = p.Sz; fp.z = p.z;
     fp.c_sk = 1.0 - p.r_sk; fp.c_fk = 1.0 - p.r_fk; fp.c_gk = 1.0 - p.r_gk; fp.c_rk = 1.0 - p.r_rk;
     const double to_mm = 1e3 / area;
@@ -49,10 +61,20 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
     const R qscale = area / (1e3 * dt), mean_scale = area / (1e3 * dt) / (double)gap;
     long n_rep = report_type == 1 ? T / gap : (T + gap - 1) / gap;
     int countdown = 0x7fffffff; long r = 0;
-    R acc = 0, agw = 0, aall = 0; double GN = 0, GD = 0;
+    R acc = 0, agw = 0, aall = 0; double GN = 0, GD = 0, riv0 = s.riv;
     for (long seg = 0; seg < 2; ++seg) {
         long n = seg == 0 ? W : T;
-        if (seg == 1) { countdown = (int)(T - (n_rep - 1) * gap); r = 0; acc = agw = aall = 0; GN = GD = 0; }
+        if (seg == 1) { countdown = (int)(T - (n_rep - 1) * gap); r = 0; acc = agw = aall = 0; GN = GD = 0; riv0 = s.riv; }
+        if (mode == 3) {   // block mode: forcing constant inside aligned blocks of `gap` steps
+            for (long day = 0; day < n / gap; ++day) {
+                const double ex_d = __dsub_rn(__dmul_rn(rain[day * gap], Tt), peva[day * gap]);
+                smart_block_fast<1>(s, fp, kc, carry, ex_d, gap, acc, agw);
+                if (seg == 1) { discharge[r++] = acc * mean_scale; GD += acc; acc = 0; }
+            }
+            if (seg == 1) { *gw_out = agw / (GD + (s.riv - riv0)); return 0; }
+            riv0 = s.riv; acc = 0; agw = 0;
+            continue;
+        }
         for (long i = 0; i < n; ++i) {
             if (mode == 0) smart_step<R, true, false>(s, p, rain[i], peva[i], o);
             else if (mode == 1) smart_step<R, false, false>(s, p, rain[i], peva[i], o);
