@@ -422,16 +422,39 @@ __device__ __forceinline__ void smart_block_fast(MemberState<double> &s, const F
         }
     } else {
         const double d0 = -ex_d;
-        // per member: if the top layer alone meets the whole block's demand the block is one
-        // subtraction, else the ladder is walked step by step (a member's arithmetic never
-        // depends on what the other lanes of its warp do)
-        const double left = s.ly[0] - d0 * static_cast<double>(rep);
-        if (sign_clear(left)) {
-            s.ly[0] = left;
-        } else {
-            const double C = kc[0];
-            for (int h = 0; h < rep; ++h) fast_dry_soil<double>(s, C, d0);
+        // Soil over the whole dry block, per member (a member's arithmetic never depends on the
+        // other lanes of its warp).  Nothing refills the layers, so each one runs empty at most
+        // once: while layers 0..k-1 are empty the demand reaching layer k is C^k d0 per step
+        // (:418), it serves floor(level / demand) whole steps in one multiplication, then one
+        // ordinary ladder step (from k down) empties it and the demand decays by C again.
+        double left = static_cast<double>(rep);      // steps of the block still to account for
+        double dem = d0;                             // demand arriving at layer k in each of them
+        const double C = kc[0];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (__any_sync(__activemask(), left > 0.0)) {
+                if (left > 0.0) {
+                    // whole steps this layer can serve; dem == 0 (C == 0) asks nothing of it
+                    const double can = dem > 0.0 ? floor(s.ly[k] / dem) : left;
+                    const double n_full = can < left ? can : left;
+                    s.ly[k] = fma(-n_full, dem, s.ly[k]);
+                    left -= n_full;
+                    if (left > 0.0) {                // transition step: layer k cannot meet the demand
+                        double d = dem;
+#pragma unroll
+                        for (int j = k; j < 6; ++j) {
+                            const double t = s.ly[j] - d;
+                            const bool enough = sign_clear(t);
+                            s.ly[j] = enough ? t : 0.0;
+                            d = enough ? 0.0 : C * (-t);
+                        }
+                        left -= 1.0;
+                        dem *= C;
+                    }
+                }
+            }
         }
+        // (after layer 5 nothing is left to take: remaining steps of the block change nothing)
         carry.valid = false;
         const double a = s.ove, b = s.itf, g = s.sgw, w = s.riv;
         const double a_n = a * kc[7 * kStride], b_n = b * kc[8 * kStride], g_n = g * kc[9 * kStride];

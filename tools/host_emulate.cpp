@@ -12,6 +12,7 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline int __double2hiint(double x) { long long v; std::memcpy(&v, &x, 8); return (int)(v >> 32); }
 static inline int __float_as_int(float x) { int v; std::memcpy(&v, &x, 4); return v; }
 using std::fma;
+using std::floor;
 static inline unsigned __activemask() { return 1u; }
 static inline int __any_sync(unsigned, int p) { return p; }
 #include "../smartpy_b200/csrc/smart_step.cuh"
