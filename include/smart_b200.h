@@ -73,7 +73,7 @@ typedef struct smart_batch_desc {
                                        of k steps with constant forcing (what the reference's daily ->
                                        hourly split produces, timeframe.py:167-186), values already per
                                        STEP (daily total / k); rows = n_steps / k.  Needs report_gap == k,
-                                       SMART_REPORT_SUMMARY, n_steps % k == n_warmup % k == 0, FP64 entry. */
+                                       SMART_REPORT_SUMMARY, n_steps % k == n_warmup % k == 0. */
     double dt_sec;                  /* simulation time step in seconds */
 
     /* ---- inputs */

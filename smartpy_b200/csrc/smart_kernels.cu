@@ -29,7 +29,8 @@ using namespace smart;
 
 constexpr int kChunkSingle = 512;  // forcing steps per smem stage, single catchment
 constexpr int kAccSlots = 8;       // per-thread binary64 accumulators parked in smem
-constexpr int kConstSlots = 14;    // per-thread R-typed constants of the fast step parked in smem
+constexpr int kConstSlots = 7;     // per-thread R-typed constants of the fast step parked in smem
+constexpr int kBlockSlots = 7;     // per-thread binary64 constants of the dry-block closed form
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
 #ifndef SMART_FAST_REGS_F64
 #define SMART_FAST_REGS_F64 96     // register budget of the fast FP64 kernel (sweep 80..104 in profiles/): 20 warps per SM, no spills
@@ -141,6 +142,7 @@ __host__ __device__ __forceinline__ int stage_doubles(int chunk, int kc) { retur
 //   double acc[kAccSlots][BLOCK]   per-thread binary64 accumulators touched once per report step
 //   R      kconst[kConstSlots][BLOCK]  per-thread constants of the fast step (see smart_step_fast)
 //   double td[BLOCK]               parameter T in binary64 (wet/dry predicate)
+//   double kblock[kBlockSlots][BLOCK]  dry-block constants (block mode only, see smart_block_fast)
 enum : int { kVariantFast = 0, kVariantGeneral = 1, kVariantFluxes = 2 };
 
 template <typename R, int BLOCK>
@@ -148,7 +150,7 @@ struct Smem {
     uint64_t *full;
     double *rain, *peva, *acc;
     R *kconst;
-    double *td;
+    double *td, *kblock;
     __device__ __forceinline__ Smem(unsigned char *raw, int tile)   // tile = stage_doubles(chunk, kc)
     {
         full = reinterpret_cast<uint64_t *>(raw);
@@ -156,7 +158,8 @@ struct Smem {
         peva = rain + 2 * tile;
         acc = peva + 2 * tile;
         kconst = reinterpret_cast<R *>(acc + kAccSlots * BLOCK);
-        td = reinterpret_cast<double *>(kconst + kConstSlots * BLOCK);
+        td = reinterpret_cast<double *>(kconst + (kConstSlots + 1) * BLOCK);   // +1: keeps 8-byte alignment for R = float
+        kblock = td + BLOCK;
     }
 };
 
@@ -316,16 +319,12 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
             const bool in_main = ci >= nWc;
             for (int i = 0; i < n; ++i) {
                 const double ex_d = __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]);   // structure.py:353-355
-                if constexpr (kFast && kWide) {
-                    smart_block_fast<BLOCK>(s, fp_, kconst, carry, ex_d, rep, acc, agw);
+                if constexpr (kFast) {
+                    smart_block_fast<R, BLOCK>(s, fp_, kconst, sm.kblock + tid, carry, ex_d, rep, acc, agw);
                 } else {
                     for (int h = 0; h < rep; ++h) {
-                        if (kFast) {
-                            smart_step_fast<R, BLOCK>(s, fp_, kconst, carry, ex_d, o);
-                        } else {
-                            smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
-                            aall += o.q_all;
-                        }
+                        smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
+                        aall += o.q_all;
                         acc += o.q_riv;
                         agw += o.q_gw;
                     }
@@ -443,14 +442,15 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         kconst[4 * BLOCK] = p.r_fk;
         kconst[5 * BLOCK] = p.r_gk;
         kconst[6 * BLOCK] = p.r_rk;
-        if (kDaily && sizeof(R) == 8) {
+        if (kDaily) {
             // closed form of a dry block of a.rep steps (smart_block_fast): c_x^rep and
-            // K_x = r_x * sum_{h<rep} c_w^(rep-1-h) c_x^h by Horner, no cancellation
+            // K_x = r_x * sum_{h<rep} c_w^(rep-1-h) c_x^h by Horner, no cancellation; binary64
             const double cx[3] = {1.0 - r_sk, 1.0 - r_fk, 1.0 - r_gk}, rx[3] = {r_sk, r_fk, r_gk};
             const double cw = 1.0 - r_rk;
+            double *kb = sm.kblock + tid;
             double pw_w = 1.0;
             for (int h = 0; h < a.rep; ++h) pw_w *= cw;
-            kconst[10 * BLOCK] = static_cast<R>(pw_w);
+            kb[3 * BLOCK] = pw_w;
 #pragma unroll
             for (int x = 0; x < 3; ++x) {
                 double G = 0.0, pxh = 1.0;
@@ -458,8 +458,8 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
                     G = fma(cw, G, pxh);
                     pxh *= cx[x];
                 }
-                kconst[(7 + x) * BLOCK] = static_cast<R>(pxh);
-                kconst[(11 + x) * BLOCK] = static_cast<R>(rx[x] * G);
+                kb[x * BLOCK] = pxh;
+                kb[(4 + x) * BLOCK] = rx[x] * G;
             }
         }
     }
@@ -885,8 +885,6 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     const int block = block_of(d);
     const int blocks = n_blocks_of(d, block);
     const bool daily = d->forcing_repeat > 1;
-    if (daily && sizeof(R) != 8)
-        return fail(SMART_ERR_BAD_ARG, "forcing_repeat > 1 is implemented for the FP64 entry point only");
     a.rep = daily ? d->forcing_repeat : 1;
     if (a.C == 1) {
         a.kc = 1;
@@ -909,7 +907,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
     const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(stage_doubles(a.chunk, a.kc)) + kAccSlots * block) +
-                        sizeof(R) * kConstSlots * block + sizeof(double) * block;
+                        sizeof(R) * (kConstSlots + 1) * block + sizeof(double) * (1 + kBlockSlots) * block;
     using Kernel = void (*)(const KArgs);
     auto go = [&](Kernel kernel) -> int {
         kernel<<<blocks, block, smem, stream>>>(a);
@@ -926,7 +924,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     auto pick = [&](auto block_tag, auto single_tag, auto daily_tag) {
         constexpr int B = decltype(block_tag)::value;
         constexpr bool S = decltype(single_tag)::value;
-        constexpr bool D = decltype(daily_tag)::value && sizeof(R) == 8;
+        constexpr bool D = decltype(daily_tag)::value;
         fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S, D>;
         fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S, D>;
         general = smart_batch_kernel<R, kVariantGeneral, B, kSlowRegs, S, D>;

@@ -397,55 +397,60 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
 //    and what left each store gives the sums by mass balance: sum Q_gw = G - G(rep),
 //    sum Q_out = (W - W(rep)) + sum_x (V_x - V_x(rep)).  Only the soil ladder is walked hour by
 //    hour, or in one subtraction when every member's top layer covers the block's demand.
-// kc slots 7..13: c_sk^rep, c_fk^rep, c_gk^rep, c_rk^rep, K_sk, K_fk, K_gk.
+// kb[] (binary64 in both precisions, one column per thread): c_sk^rep, c_fk^rep, c_gk^rep,
+// c_rk^rep, K_sk, K_fk, K_gk.  The dry block is evaluated in binary64 also for binary32 state:
+// it costs ~40 instructions per BLOCK, and binary32 powers of (1 - dt/k) would bias the recession.
 // acc += sum of river outflow over the block, agw += sum of groundwater outflow (mm).
-template <int kStride>
-__device__ __forceinline__ void smart_block_fast(MemberState<double> &s, const FastPar<double> &p, const double *kc,
-                                                 FastCarry<double> &carry, double ex_d, int rep, double &acc,
-                                                 double &agw)
+template <typename R, int kStride>
+__device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPar<R> &p, const R *kc, const double *kb,
+                                                 FastCarry<R> &carry, double ex_d, int rep, R &acc, R &agw)
 {
+    constexpr bool kOneFma = sizeof(R) == 8;
     if (ex_d >= 0.0) {
+        const R ex = static_cast<R>(ex_d);
         for (int h = 0; h < rep; ++h) {
-            const double q_quick = s.ove * kc[3 * kStride];
-            const double q_int = s.itf * kc[4 * kStride];
-            const double q_gw = s.sgw * kc[5 * kStride];
-            const double q = s.riv * kc[6 * kStride];
-            const double q_in = (q_quick + q_int) + q_gw;
-            s.riv = fma(s.riv, p.c_rk, q_in);
+            const R q_quick = s.ove * kc[3 * kStride];
+            const R q_int = s.itf * kc[4 * kStride];
+            const R q_gw = s.sgw * kc[5 * kStride];
+            const R q = s.riv * kc[6 * kStride];
+            const R q_in = (q_quick + q_int) + q_gw;
+            s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - q) + q_in;
             acc += q;
             agw += q_gw;
-            double in_quick, in_int, in_gw;
-            fast_wet_soil<double, kStride>(s, p, kc, carry, ex_d, in_quick, in_int, in_gw);
-            s.ove = fma(s.ove, p.c_sk, in_quick);
-            s.itf = fma(s.itf, p.c_fk, in_int);
-            s.sgw = fma(s.sgw, p.c_gk, in_gw);
+            R in_quick, in_int, in_gw;
+            fast_wet_soil<R, kStride>(s, p, kc, carry, ex, in_quick, in_int, in_gw);
+            s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - q_quick) + in_quick;
+            s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - q_int) + in_int;
+            s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
         }
     } else {
-        const double d0 = -ex_d;
         // Soil over the whole dry block, per member (a member's arithmetic never depends on the
         // other lanes of its warp).  Nothing refills the layers, so each one runs empty at most
         // once: while layers 0..k-1 are empty the demand reaching layer k is C^k d0 per step
         // (:418), it serves floor(level / demand) whole steps in one multiplication, then one
         // ordinary ladder step (from k down) empties it and the demand decays by C again.
         double left = static_cast<double>(rep);      // steps of the block still to account for
-        double dem = d0;                             // demand arriving at layer k in each of them
-        const double C = kc[0];
+        double dem = -ex_d;                          // demand arriving at layer k in each of them
+        const double C = static_cast<double>(kc[0]);
+        double ly[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ly[k] = static_cast<double>(s.ly[k]);
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             if (__any_sync(__activemask(), left > 0.0)) {
                 if (left > 0.0) {
                     // whole steps this layer can serve; dem == 0 (C == 0) asks nothing of it
-                    const double can = dem > 0.0 ? floor(s.ly[k] / dem) : left;
+                    const double can = dem > 0.0 ? floor(ly[k] / dem) : left;
                     const double n_full = can < left ? can : left;
-                    s.ly[k] = fma(-n_full, dem, s.ly[k]);
+                    ly[k] = fma(-n_full, dem, ly[k]);
                     left -= n_full;
                     if (left > 0.0) {                // transition step: layer k cannot meet the demand
                         double d = dem;
 #pragma unroll
                         for (int j = k; j < 6; ++j) {
-                            const double t = s.ly[j] - d;
+                            const double t = ly[j] - d;
                             const bool enough = sign_clear(t);
-                            s.ly[j] = enough ? t : 0.0;
+                            ly[j] = enough ? t : 0.0;
                             d = enough ? 0.0 : C * (-t);
                         }
                         left -= 1.0;
@@ -455,17 +460,20 @@ __device__ __forceinline__ void smart_block_fast(MemberState<double> &s, const F
             }
         }
         // (after layer 5 nothing is left to take: remaining steps of the block change nothing)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(ly[k]);
         carry.valid = false;
-        const double a = s.ove, b = s.itf, g = s.sgw, w = s.riv;
-        const double a_n = a * kc[7 * kStride], b_n = b * kc[8 * kStride], g_n = g * kc[9 * kStride];
-        const double w_n = fma(kc[11 * kStride], a, fma(kc[12 * kStride], b, fma(kc[13 * kStride], g, w * kc[10 * kStride])));
+        const double a = static_cast<double>(s.ove), b = static_cast<double>(s.itf);
+        const double g = static_cast<double>(s.sgw), w = static_cast<double>(s.riv);
+        const double a_n = a * kb[0 * kStride], b_n = b * kb[1 * kStride], g_n = g * kb[2 * kStride];
+        const double w_n = fma(kb[4 * kStride], a, fma(kb[5 * kStride], b, fma(kb[6 * kStride], g, w * kb[3 * kStride])));
         const double out_g = g - g_n;
-        agw += out_g;
-        acc += ((w - w_n) + (a - a_n)) + ((b - b_n) + out_g);
-        s.ove = a_n;
-        s.itf = b_n;
-        s.sgw = g_n;
-        s.riv = w_n;
+        agw += static_cast<R>(out_g);
+        acc += static_cast<R>(((w - w_n) + (a - a_n)) + ((b - b_n) + out_g));
+        s.ove = static_cast<R>(a_n);
+        s.itf = static_cast<R>(b_n);
+        s.sgw = static_cast<R>(g_n);
+        s.riv = static_cast<R>(w_n);
     }
 }
 

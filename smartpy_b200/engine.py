@@ -158,7 +158,7 @@ class BatchEngine(object):
         """Does this run qualify for one forcing row per reporting step (include/smart_b200.h)?"""
         k = self._repeat
         return (k > 1 and k == self.report_gap and self.report_type == _native.REPORT_SUMMARY and
-                self.precision == 'f64' and self.warm_up_steps % k == 0 and initial_state is None and
+                self.warm_up_steps % k == 0 and initial_state is None and
                 not last_state and not (self.flags & FLAG_NO_BLOCK_MODE))
 
     # ------------------------------------------------------------------ descriptor

@@ -31,17 +31,18 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
     MemberPar<R> p;
     p.Td = Tt; p.C = C; p.D = D; p.omD = 1.0 - D; p.Hz = H / Z; p.Sz = S / Z; p.z = Z / 6.0;
     p.r_sk = dt / (SK * 3600.0); p.r_fk = dt / (FK * 3600.0); p.r_gk = dt / (GK * 3600.0); p.r_rk = dt / (RK * 3600.0);
-    R kc[14] = {C, D, 1.0 - D, p.r_sk, p.r_fk, p.r_gk, p.r_rk};
+    R kc[7] = {C, D, 1.0 - D, p.r_sk, p.r_fk, p.r_gk, p.r_rk};
+    double kb[7];
     {
         const double cx[3] = {1.0 - p.r_sk, 1.0 - p.r_fk, 1.0 - p.r_gk}, rx[3] = {p.r_sk, p.r_fk, p.r_gk};
         const double cw = 1.0 - p.r_rk;
         double pw_w = 1.0;
         for (int h = 0; h < gap; ++h) pw_w *= cw;
-        kc[10] = pw_w;
+        kb[3] = pw_w;
         for (int x = 0; x < 3; ++x) {
             double G = 0.0, pxh = 1.0;
             for (int h = 0; h < gap; ++h) { G = fma(cw, G, pxh); pxh *= cx[x]; }
-            kc[7 + x] = pxh; kc[11 + x] = rx[x] * G;
+            kb[x] = pxh; kb[4 + x] = rx[x] * G;
         }
     }
     FastPar<R> fp; fp.Hz = p.Hz; fp.Sz = p.Sz; fp.z = p.z;
@@ -69,7 +70,7 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
         if (mode == 3) {   // block mode: forcing constant inside aligned blocks of `gap` steps
             for (long day = 0; day < n / gap; ++day) {
                 const double ex_d = __dsub_rn(__dmul_rn(rain[day * gap], Tt), peva[day * gap]);
-                smart_block_fast<1>(s, fp, kc, carry, ex_d, gap, acc, agw);
+                smart_block_fast<R, 1>(s, fp, kc, kb, carry, ex_d, gap, acc, agw);
                 if (seg == 1) { discharge[r++] = acc * mean_scale; GD += acc; acc = 0; }
             }
             if (seg == 1) { *gw_out = agw / (GD + (s.riv - riv0)); return 0; }
