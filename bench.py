@@ -397,12 +397,12 @@ def main():
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     # DRAM traffic of the dominant kernel per launch, from the committed ncu --set full capture
-    traffic = None
+    traffic, ncu = None, {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            t = json.load(f).get("{}:{}".format(args.workload, n))
-        if t:
-            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+            ncu = json.load(f).get("{}:{}:{}".format(args.workload, n, precision)) or {}
+        if ncu:
+            traffic = ncu["dram_bytes_read"] + ncu["dram_bytes_write"]
     except (OSError, ValueError, KeyError):
         pass
     roofline = {
@@ -415,6 +415,13 @@ def main():
         "peak_nominal": 148 * (64 if bits == 64 else 128) * 1.965e9 / 1e12,
         "traffic": traffic,
         "algorithmic_bytes": hbm_bytes_per_step,
+        # `frac` follows the contract (algorithmic work of the per-step restatement / time); the
+        # kernel executes fewer FP64 instructions than that (merged stores, closed-form dry blocks),
+        # so the pipe's own utilisation is given beside it from the committed ncu capture
+        "executed": ({"fp64_warp_inst_per_warp_step": ncu["fp64_inst_per_step"],
+                      "frac_of_peak": per_gpu * ncu["fp64_inst_per_step"] / peak_fma,
+                      "ncu_fp64_pipe_active_pct": ncu.get("fp64_pipe_active_pct"),
+                      "source": ncu.get("source")} if ncu.get("fp64_inst_per_step") else None),
         "hbm": {"achieved_gbs": hbm_bytes_per_step / (ms_per_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": hbm_bytes_per_step / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},

@@ -895,7 +895,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     } else {
         a.kc = (block - 1) / a.mpc + 2;              // catchments one CTA can straddle
         if (a.kc > a.C) a.kc = a.C;
-        int chunk = (block == kBlockLarge ? 24 * 1024 : 12 * 1024) / (2 * 2 * 8 * a.kc);
+        int chunk = (12 * 1024) / (2 * 2 * 8 * a.kc);   // 12 KB of forcing stages per CTA
         chunk = chunk > (daily ? 64 : 512) ? (daily ? 64 : 512) : chunk;
         chunk &= ~7;
         if (chunk < 8) return fail(SMART_ERR_BAD_ARG, "members_per_catchment too small for one CTA tile");
@@ -907,9 +907,11 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
     const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(stage_doubles(a.chunk, a.kc)) + kAccSlots * block) +
-                        sizeof(R) * (kConstSlots + 1) * block + sizeof(double) * (1 + kBlockSlots) * block;
+                        sizeof(R) * (kConstSlots + 1) * block + sizeof(double) * (1 + (daily ? kBlockSlots : 0)) * block;
     using Kernel = void (*)(const KArgs);
     auto go = [&](Kernel kernel) -> int {
+        if (smem > 48 * 1024)   // above the default dynamic shared memory limit: opt in per kernel
+            SMART_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         kernel<<<blocks, block, smem, stream>>>(a);
         SMART_CUDA(cudaGetLastError());
         return SMART_OK;

@@ -372,3 +372,23 @@ def test_general_kernel_on_out_of_range_members(catchment, oracle_lib):
                                   EXTRA, n_steps, 24, warm_up=20)
         scale = np.maximum(np.abs(q_ref), 1e-9 * np.abs(q_ref).max())
         assert np.max(np.abs(q[m] - q_ref) / scale) < RTOL_Q
+
+
+def test_large_multi_catchment_batch_uses_wide_ctas(catchment, oracle_lib):
+    """> 871k members: 128-member CTAs, three catchments per tile (needs > 48 KB of shared memory)."""
+    _torch()
+    from smartpy_b200.engine import BatchEngine
+    n_catch, mpc, n_steps = 9000, 100, 48
+    rng = np.random.RandomState(5)
+    rain = np.ascontiguousarray(np.tile(catchment.rain[3000:3000 + n_steps, None], (1, n_catch)) * rng.uniform(0.5, 1.5, n_catch))
+    peva = np.ascontiguousarray(np.tile(catchment.peva[3000:3000 + n_steps, None], (1, n_catch)))
+    area = rng.uniform(1e7, 1e9, n_catch)
+    base = load_golden("runs_members")["params"]
+    params = np.resize(base, (n_catch * mpc, 10))
+    eng = BatchEngine(rain, peva, area, 3600.0, 1, extra=EXTRA, report='raw', members_per_catchment=mpc)
+    q = eng.run(params, discharge=True, scores=False)["discharge"]
+    for m in (0, 123457, n_catch * mpc - 1):
+        c = m // mpc
+        q_ref, _ = oracle_lib.run(area[c], 3600.0, rain[:, c].copy(), peva[:, c].copy(), params[m], EXTRA, n_steps, 1,
+                                  report='raw')
+        assert relmax(q[:, m].cpu().numpy(), q_ref) < RTOL_Q
