@@ -1111,8 +1111,9 @@ int smart_batch_run_host(const smart_batch_desc *h, int precision, int device)
         return SMART_OK;
     };
     if ((rc = up(params, h->params, sizeof(double) * N * SMART_N_PARAMS, (const void **)&d.params))) return rc;
-    if ((rc = up(rain, h->rain, sizeof(double) * T * C, (const void **)&d.rain))) return rc;
-    if ((rc = up(peva, h->peva, sizeof(double) * T * C, (const void **)&d.peva))) return rc;
+    const int64_t rows = h->forcing_repeat > 1 ? T / h->forcing_repeat : T;   // one row per block of steps
+    if ((rc = up(rain, h->rain, sizeof(double) * rows * C, (const void **)&d.rain))) return rc;
+    if ((rc = up(peva, h->peva, sizeof(double) * rows * C, (const void **)&d.peva))) return rc;
     if ((rc = up(area, h->area_m2, sizeof(double) * C, (const void **)&d.area_m2))) return rc;
     if (h->initial_state &&
         (rc = up(init, h->initial_state, sizeof(double) * N * SMART_N_VARS, (const void **)&d.initial_state)))

@@ -45,10 +45,18 @@ struct StepOut {
     R aeva, q_ove, q_dra, q_int, q_sgw, q_dgw;   // mm per step
 };
 
+// 1/(i+1) for the shallow-groundwater leak (structure.py:389).  The binary64 values that are not
+// exact FP64 immediates live in constant memory so that they are operands of the multiply itself
+// instead of being rebuilt with UMOV pairs every wet step.
+#ifndef SMART_HOST_EMULATION
+__device__ __constant__ double smart_inv3 = 1.0 / 3.0, smart_inv5 = 0.2, smart_inv6 = 1.0 / 6.0;
+#else
+static const double smart_inv3 = 1.0 / 3.0, smart_inv5 = 0.2, smart_inv6 = 1.0 / 6.0;
+#endif
 template <typename R> __device__ __forceinline__ R inv_const(int i);
 template <> __device__ __forceinline__ double inv_const<double>(int i)
 {
-    return i == 0 ? 1.0 : i == 1 ? 0.5 : i == 2 ? (1.0 / 3.0) : i == 3 ? 0.25 : i == 4 ? 0.2 : (1.0 / 6.0);
+    return i == 0 ? 1.0 : i == 1 ? 0.5 : i == 2 ? smart_inv3 : i == 3 ? 0.25 : i == 4 ? smart_inv5 : smart_inv6;
 }
 template <> __device__ __forceinline__ float inv_const<float>(int i)
 {
@@ -245,7 +253,7 @@ __device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >
 // Wet hour, soil part (structure.py:360-399): overland split, fill ladder, saturation excess,
 // three leak passes.  ex = rain * T - peva >= 0.  Returns the three merged inflows.
 template <typename R, int kStride>
-__device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R> &p, const R *kc,
+__device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R> &p, R D, R omD,
                                               FastCarry<R> &carry, R ex, R &in_quick, R &in_int, R &in_gw)
 {
     constexpr bool kLeakByDifference = sizeof(R) == 8;
@@ -272,8 +280,8 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
 #else
     fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
 #endif
-    in_quick = fma(kc[1 * kStride], -u, in_quick);  // + D * saturation excess (:376)
-    in_int = kc[2 * kStride] * (-u);                // (1 - D) * saturation excess (:377)
+    in_quick = fma(D, -u, in_quick);                // + D * saturation excess (:376)
+    in_int = omD * (-u);                            // (1 - D) * saturation excess (:377)
     const R sp = p.Sz * tot;                        // :379
     R pw[6];
     pw[0] = sp;
@@ -372,7 +380,8 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
     o.q_riv = q;
 
     if (ex_d >= 0.0) {
-        fast_wet_soil<R, kStride>(s, p, kc, carry, static_cast<R>(ex_d), in_quick, in_int, in_gw);
+        fast_wet_soil<R, kStride>(s, p, kc[1 * kStride], kc[2 * kStride], carry, static_cast<R>(ex_d), in_quick, in_int,
+                                  in_gw);
     } else {
         fast_dry_soil<R>(s, kc[0], static_cast<R>(-ex_d));
         carry.valid = false;
@@ -408,6 +417,7 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
     constexpr bool kOneFma = sizeof(R) == 8;
     if (ex_d >= 0.0) {
         const R ex = static_cast<R>(ex_d);
+        const R D = kc[1 * kStride], omD = kc[2 * kStride];
         for (int h = 0; h < rep; ++h) {
             const R q_quick = s.ove * kc[3 * kStride];
             const R q_int = s.itf * kc[4 * kStride];
@@ -418,7 +428,7 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
             acc += q;
             agw += q_gw;
             R in_quick, in_int, in_gw;
-            fast_wet_soil<R, kStride>(s, p, kc, carry, ex, in_quick, in_int, in_gw);
+            fast_wet_soil<R, kStride>(s, p, D, omD, carry, ex, in_quick, in_int, in_gw);
             s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - q_quick) + in_quick;
             s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - q_int) + in_int;
             s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
