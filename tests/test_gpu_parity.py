@@ -392,3 +392,27 @@ def test_large_multi_catchment_batch_uses_wide_ctas(catchment, oracle_lib):
         q_ref, _ = oracle_lib.run(area[c], 3600.0, rain[:, c].copy(), peva[:, c].copy(), params[m], EXTRA, n_steps, 1,
                                   report='raw')
         assert relmax(q[:, m].cpu().numpy(), q_ref) < RTOL_Q
+
+
+# ---------------------------------------------------------------- BASELINE config 3 shape: 30 years hourly
+@pytest.mark.parametrize("flags", [0, 0x10000])     # block mode, per-step path
+def test_thirty_year_synthetic_forcing_matches_oracle(oracle_lib, flags):
+    """262,992 + 8,760 steps of the synthetic forcing bench.py uses for C3, a few
+    members against the oracle, scores included: errors must not grow with the length of the run."""
+    _torch()
+    import bench
+    from smartpy_b200.engine import BatchEngine
+    from oracle import scores as oscores
+    w = bench.make_workload("c3", 0, members=64)
+    params = w["params"][[0, 9, 17, 31, 42, 63]]
+    eng = BatchEngine(w["rain"], w["peva"], w["area"], w["dt"], w["gap"], obs=w["obs"], extra=w["extra"],
+                      warm_up_steps=w["warm_steps"], gw_constraint=w["gwc"], flags=flags)
+    res = eng.run(params, discharge=True, scores=True, gw=True)
+    q = res["discharge"].cpu().numpy().T
+    sc = res["scores"].cpu().numpy()
+    q_ref, gw_ref = oracle_lib.run_members(w["area"], w["dt"], w["rain"], w["peva"], params, w["extra"], w["n_steps"],
+                                           w["gap"], warm_up=365)
+    assert relmax(q, q_ref) < RTOL_Q
+    sc_ref = oscores.score_members(q_ref, gw_ref, w["obs"], w["gwc"])
+    assert np.max(np.abs(sc[:, :7] - sc_ref[:, :7]) / np.maximum(1.0, np.abs(sc_ref[:, :7]))) < 1e-10
+    assert np.array_equal(sc[:, 7], sc_ref[:, 7])
