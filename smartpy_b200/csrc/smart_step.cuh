@@ -410,6 +410,11 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
 // c_rk^rep, K_sk, K_fk, K_gk.  The dry block is evaluated in binary64 also for binary32 state:
 // it costs ~40 instructions per BLOCK, and binary32 powers of (1 - dt/k) would bias the recession.
 // acc += sum of river outflow over the block, agw += sum of groundwater outflow (mm).
+#ifndef SMART_WET_UNROLL
+#define SMART_WET_UNROLL 4
+#endif
+constexpr int kWetUnroll = SMART_WET_UNROLL;   // unroll factor of the wet-block hour loop
+
 template <typename R, int kStride>
 __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPar<R> &p, const R *kc, const double *kb,
                                                  FastCarry<R> &carry, double ex_d, int rep, R &acc, R &agw)
@@ -418,6 +423,7 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
     if (ex_d >= 0.0) {
         const R ex = static_cast<R>(ex_d);
         const R D = kc[1 * kStride], omD = kc[2 * kStride];
+#pragma unroll kWetUnroll
         for (int h = 0; h < rep; ++h) {
             const R q_quick = s.ove * kc[3 * kStride];
             const R q_int = s.itf * kc[4 * kStride];
