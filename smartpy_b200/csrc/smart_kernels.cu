@@ -32,6 +32,10 @@ constexpr int kAccSlots = 8;       // per-thread binary64 accumulators parked in
 constexpr int kConstSlots = 7;     // per-thread R-typed constants of the fast step parked in smem
 constexpr int kBlockSlots = 7;     // per-thread binary64 constants of the dry-block closed form
 constexpr int kSmemHeader = 128;   // two mbarriers, padded
+#ifndef SMART_STEP_UNROLL
+#define SMART_STEP_UNROLL 1
+#endif
+constexpr int kStepUnroll = SMART_STEP_UNROLL;   // unroll factor of the per-step time loop
 #ifndef SMART_FAST_REGS_F64
 #define SMART_FAST_REGS_F64 96     // register budget of the fast FP64 kernel (sweep 80..104 in profiles/): 20 warps per SM, no spills
 #endif
@@ -341,6 +345,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         } else {
             // wet/dry driver of the fast step, formed one step ahead of the state
             double ex_next = kFast ? __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]) : 0.0;
+#pragma unroll kStepUnroll
             for (int i = 0; i < n; ++i) {
                 if (kFast) {
                     const double ex_d = ex_next;
