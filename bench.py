@@ -399,7 +399,7 @@ def main():
     traffic, ncu = None, {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            ncu = json.load(f).get("{}:{}:{}".format(args.workload, n, precision)) or {}
+            ncu = json.load(f).get("{}:{}:{}:{}".format(args.workload, n, precision, args.flags)) or {}
         if ncu:
             traffic = ncu["dram_bytes_read"] + ncu["dram_bytes_write"]
     except (OSError, ValueError, KeyError):
