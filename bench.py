@@ -11,6 +11,7 @@ objective functions fused, scores only) on synthetic/fixture forcing:
       test catchment (2007-2016 hourly, 87,672 steps + 8,760 warm-up), NSE/KGE/... scored.
   c3: 30-year hourly synthetic forcing (262,992 + 8,760 steps), 1.25e6 members per GPU.
   c4a: 1e4 synthetic catchments x 100 members, [t][catchment] forcing, hourly discharge written.
+  c4b: same catchments, 10 years from daily totals split on the device, daily discharge written.
   c5: c2 shape in FP32 state (--precision f32).
 
 With N > 1 (torchrun, one rank per GPU) every rank runs the same per-GPU batch on its own
@@ -111,11 +112,27 @@ def make_workload(name, rank, members=None):
         n = n_catch * mpc
         w["label"] = "{} synthetic catchments x {} members, [t][catchment] forcing, hourly discharge written".format(
             n_catch, mpc)
+    elif name == "c4b":
+        # daily totals in, split on the device (forcing_repeat): 10 years, daily discharge written
+        n_catch, mpc = (members // 100 if members else 10000), 100
+        n_days = 3653
+        rain = np.empty((n_days, n_catch))
+        peva = np.empty((n_days, n_catch))
+        for c in range(n_catch):
+            r, p = synthetic_forcing(n_days, rank * n_catch + c)
+            rain[:, c], peva[:, c] = r[::24] * 24.0, p[::24] * 24.0
+        rng = np.random.Generator(np.random.PCG64(7))
+        area = np.exp(rng.uniform(np.log(10e6), np.log(2000e6), n_catch))
+        w.update(rain=rain, peva=peva, obs=None, area=area, gap=24, warm_steps=0, discharge=True, mpc=mpc, gwc=None,
+                 forcing_repeat=24)
+        n = n_catch * mpc
+        w["label"] = ("{} synthetic catchments x {} members, daily [t][catchment] forcing split on the device, "
+                      "10 yr hourly, daily discharge written").format(n_catch, mpc)
     else:
         raise SystemExit("unknown workload " + name)
     w["params"] = lhs_rows(n, 42 + rank)
     w["n_members"] = n
-    w["n_steps"] = w["rain"].shape[0]
+    w["n_steps"] = w["rain"].shape[0] * w.get("forcing_repeat", 1)
     w["name"] = name
     return w
 
@@ -124,7 +141,8 @@ def wet_fraction(w):
     """Fraction of member-steps taking the wet branch (T in 0.9..1.1, midpoint 1.0 used)."""
     rain = w["rain"] if w["rain"].ndim == 1 else w["rain"][:, 0]
     peva = w["peva"] if w["peva"].ndim == 1 else w["peva"][:, 0]
-    seq = np.concatenate([rain[:w["warm_steps"]], rain]), np.concatenate([peva[:w["warm_steps"]], peva])
+    k = w.get("forcing_repeat", 1)
+    seq = (np.concatenate([rain[:w["warm_steps"] // k], rain]), np.concatenate([peva[:w["warm_steps"] // k], peva]))
     return float(np.mean(seq[0] * 1.0 - seq[1] >= 0.0))
 
 
@@ -243,7 +261,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4a", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4a", "c4b", "c5"])
     ap.add_argument("--precision", default=None, choices=["f64", "f32"])
     ap.add_argument("--members", type=int, default=None, help="members per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -277,7 +295,8 @@ def main():
     n = w["n_members"]
     eng = BatchEngine(w["rain"], w["peva"], w["area"], w["dt"], w["gap"], obs=w.get("obs"), extra=w["extra"],
                       warm_up_steps=w["warm_steps"], report=w["report"], gw_constraint=w["gwc"],
-                      members_per_catchment=w["mpc"], precision=precision, flags=args.flags)
+                      members_per_catchment=w["mpc"], precision=precision, flags=args.flags,
+                      forcing_repeat=w.get("forcing_repeat", 1))
     member_steps = eng.member_steps(n)             # per rank per step
     scored = w.get("obs") is not None
     stream = torch.cuda.current_stream(dev)
@@ -386,7 +405,7 @@ def main():
     i_alg = I_DRY + (I_WET - I_DRY) * wfrac
     per_gpu = value / world
     achieved = per_gpu * i_alg
-    hbm_bytes_per_step = (n * (80 + 64 + 8) + 2 * 8 * (w["n_steps"]) +
+    hbm_bytes_per_step = (n * (80 + 64 + 8) + 2 * 8 * w["rain"].size +
                           (eng.n_report * n * (8 if precision == "f64" else 4) if w["discharge"] else 0))
     peaks = {}
     try:
