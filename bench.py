@@ -448,7 +448,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": precision, "data": "synthetic" if args.workload in ("c3", "c4a") else
+        "vs_baseline": None, "dtype": precision, "data": "synthetic" if args.workload in ("c3", "c4a", "c4b") else
         "reference test catchment forcing (tests/golden fixture) + LHS parameter sets (seed 42 + rank)",
         "config": {"workload": "{}: {}".format(args.workload, w["label"]), "members_per_gpu": n,
                    "steps_per_member": w["n_steps"] + w["warm_steps"], "report_gap": w["gap"],
