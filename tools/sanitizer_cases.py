@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Small runs of every kernel path, meant to be executed under compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python tools/sanitizer_cases.py
+    compute-sanitizer --tool racecheck python tools/sanitizer_cases.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from conftest import Catchment, load_golden, EXTRA  # noqa: E402
+from smartpy_b200.engine import BatchEngine  # noqa: E402
+
+
+def main():
+    import torch
+    c = Catchment()
+    g = load_golden("runs_members")
+    days = 40
+    n = days * 24
+    obs = c.obs[:days]
+    params = np.resize(g["params"], (150, 10))
+    cases = []
+    for flags in (0, 0x10000, 0x10002, 1):
+        for precision in ('f64', 'f32'):
+            eng = BatchEngine(c.rain[:n], c.peva[:n], c.area, 3600.0, 24, obs=obs, extra=EXTRA, warm_up_steps=24 * 5,
+                              gw_constraint=0.12667, precision=precision, flags=flags)
+            r = eng.run(params, discharge=True, scores=True, gw=True, best=('NSE', 1))
+            cases.append(("flags=%#x %s" % (flags, precision), float(r["scores"][:, 0].max())))
+    # odd lengths, raw reporting, last_state / initial_state (fluxes kernel)
+    eng = BatchEngine(c.rain[7:7 + 777], c.peva[7:7 + 777], c.area, 3600.0, 7, extra=EXTRA, warm_up_steps=49, report='raw')
+    r = eng.run(params[:5], discharge=True, scores=False, last_state=True)
+    eng.run(params[:5], discharge=True, scores=False, initial_state=r["last_state"].cpu().numpy())
+    # multi-catchment tiles (cp.async path), per-step and block mode
+    rain = np.stack([c.rain[:n] * k for k in (1.0, 0.7, 1.3)], 1)
+    peva = np.stack([c.peva[:n]] * 3, 1)
+    for mpc in (50, 7):
+        eng = BatchEngine(rain, peva, [1e8, 2e8, 3e8], 3600.0, 24, extra=EXTRA, members_per_catchment=mpc)
+        eng.run(params[:3 * mpc], discharge=True, scores=False)
+        eng = BatchEngine(rain[5:5 + 24 * 30], peva[5:5 + 24 * 30], [1e8, 2e8, 3e8], 3600.0, 1, report='raw',
+                          members_per_catchment=mpc)
+        eng.run(params[:3 * mpc], discharge=True, scores=False)
+    torch.cuda.synchronize()
+    for name, v in cases:
+        print(name, v)
+    print("sanitizer cases done")
+
+
+if __name__ == "__main__":
+    main()
