@@ -1,0 +1,45 @@
+"""CPU: the CUDA step header (smartpy_b200/csrc/smart_step.cuh) compiled for the HOST with g++
+(tools/host_emulate.cpp, a development aid -- never loaded by smartpy_b200) against the
+reference-generated goldens.  This checks the arithmetic of the three step formulations (general,
+per-step fast, block mode) without a GPU; the GPU tests check the kernels themselves.  On B200
+the kernels reproduce these host numbers to the last digit (profiles/r01_parity_report.txt)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+
+
+@pytest.fixture(scope="module")
+def emulator(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("emul") / "libemul.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-DSMART_HOST_EMULATION", "-shared", "-fPIC", "-o", so,
+                           os.path.join(ROOT, "tools", "host_emulate.cpp")])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.emulate_run.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_long, ctypes.c_long, dp, dp, dp,
+                                ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_int, dp, dp]
+    return lib
+
+
+@pytest.mark.parametrize("mode,label,bound", [(0, "general", 2e-12), (2, "per-step fast", 4e-12), (3, "block mode", 8e-12)])
+def test_step_formulations_match_reference_goldens(emulator, catchment, mode, label, bound):
+    dp = ctypes.POINTER(ctypes.c_double)
+    g = load_golden("runs_members")
+    split = np.array([0.10, 0.15, 0.15, 0.30, 0.30])
+    rain, peva = np.ascontiguousarray(catchment.rain), np.ascontiguousarray(catchment.peva)
+    worst_q = worst_gw = 0.0
+    for i, p in enumerate(g["params"]):
+        q = np.zeros(3653)
+        gw = ctypes.c_double()
+        p = np.ascontiguousarray(p)
+        emulator.emulate_run(mode, catchment.area, 3600.0, 87672, 8760, rain.ctypes.data_as(dp), peva.ctypes.data_as(dp),
+                             p.ctypes.data_as(dp), 1, 1200 * 0.45, split.ctypes.data_as(dp), 1, 24,
+                             q.ctypes.data_as(dp), ctypes.byref(gw))
+        worst_q = max(worst_q, float(np.max(np.abs(q - g["q"][i]) / g["q"][i])))
+        worst_gw = max(worst_gw, abs(gw.value - g["gw"][i]) / g["gw"][i])
+    assert worst_q < bound, (label, worst_q)        # far inside the 1e-10 bar of BASELINE.json
+    assert worst_gw < 1e-11
