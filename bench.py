@@ -30,7 +30,6 @@ oracle's C restatement of it (bit-identical discharge, ~80x faster than the Pyth
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
