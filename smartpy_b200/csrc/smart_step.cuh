@@ -64,6 +64,12 @@ template <> __device__ __forceinline__ float inv_const<float>(int i)
     return i == 0 ? 1.0f : i == 1 ? 0.5f : i == 2 ? (1.0f / 3.0f) : i == 3 ? 0.25f : i == 4 ? 0.2f : (1.0f / 6.0f);
 }
 
+// x >= 0 for a freshly computed difference x = a - b of finite values, read from the sign bit on
+// the integer pipe instead of an FP64 compare.  Exact: rounding never changes the sign of a
+// difference, and a - b is +0 (sign clear) when a == b.
+__device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
+__device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >= 0; }
+
 // kGeneral = true : branch-faithful form -- five separate reservoirs with the >= 0 clamps
 //                   (:427-450), the 95 % river cap (:492-498) and the `leak < level`
 //                   predicates (:383, :390, :397).  Needed when dt > k for some store, when
@@ -77,8 +83,6 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
                                            double rain, double peva, StepOut<R> &o)
 {
     const R zero = R(0);
-    // structure.py:350 -- left-to-right sum of the six layer levels
-    R tot = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
 
     // structure.py:353-359 -- binary64, separately rounded
     const double rain_c = __dmul_rn(rain, p.Td);
@@ -90,16 +94,21 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
         // ---- wet branch, structure.py:360-399
         R ex = static_cast<R>(ex_d);
         if (kFluxes) o.aeva = static_cast<R>(peva);   // :361
+        // structure.py:350 -- left-to-right sum of the six layer levels (only the wet branch reads it)
+        const R tot = ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
         in_ove = (p.Hz * tot) * ex;                 // :363-364
         ex = ex - in_ove;                           // :365
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {               // :367-374
+        auto fill = [&](int i) {                    // :367-374, `ex <= space` as the sign of space - ex
             const R space = p.z - s.ly[i];
-            const bool fits = ex <= space;
-            const R add = fits ? ex : space;
-            s.ly[i] = fits ? s.ly[i] + add : p.z;
-            ex = ex - add;
-        }
+            const R t = space - ex;
+            const bool fits = sign_clear(t);
+            s.ly[i] = fits ? s.ly[i] + ex : p.z;
+            ex = fits ? zero : -t;                  // -(space - ex) is exactly ex - space
+            return fits;
+        };
+        // (no early-out here: with caller-supplied initial states a lower layer may be over-full,
+        // and the reference then moves water down even when nothing arrives from above)
+        fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
         in_dra = p.D * ex;                          // :376
         in_int = p.omD * ex;                        // :377
         const R sp = p.Sz * tot;                    // :379 (start-of-step total)
@@ -141,7 +150,7 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const R t = s.ly[i] - d;
-            const bool enough = !(t < zero);        // level >= deficit
+            const bool enough = sign_clear(t);      // level >= deficit
             if (kFluxes) aeva += enough ? d : s.ly[i];   // :412, :415
             s.ly[i] = enough ? t : zero;
             d = enough ? zero : p.C * (-t);
@@ -153,19 +162,19 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
         // structure.py:427-450 -- outflow from the OLD storage, then update, then clamp
         const R q_ove = s.ove * p.r_sk;
         s.ove = s.ove + (in_ove - q_ove);
-        if (s.ove < zero) s.ove = zero;
+        if (!sign_clear(s.ove)) s.ove = zero;
         const R q_dra = s.dra * p.r_sk;
         s.dra = s.dra + (in_dra - q_dra);
-        if (s.dra < zero) s.dra = zero;
+        if (!sign_clear(s.dra)) s.dra = zero;
         const R q_int = s.itf * p.r_fk;
         s.itf = s.itf + (in_int - q_int);
-        if (s.itf < zero) s.itf = zero;
+        if (!sign_clear(s.itf)) s.itf = zero;
         const R q_sgw = s.sgw * p.r_gk;
         s.sgw = s.sgw + (in_sgw - q_sgw);
-        if (s.sgw < zero) s.sgw = zero;
+        if (!sign_clear(s.sgw)) s.sgw = zero;
         const R q_dgw = s.dgw * p.r_gk;
         s.dgw = s.dgw + (in_dgw - q_dgw);
-        if (s.dgw < zero) s.dgw = zero;
+        if (!sign_clear(s.dgw)) s.dgw = zero;
         o.q_gw = q_sgw + q_dgw;
         if (kFluxes) {
             o.q_ove = q_ove;
@@ -179,7 +188,7 @@ __device__ __forceinline__ void smart_step(MemberState<R> &s, const MemberPar<R>
         // structure.py:482-498
         R q = s.riv * p.r_rk;
         const R tmp = s.riv + (q_in - q);
-        if (tmp < zero) {
+        if (!sign_clear(tmp)) {
             q = R(0.95) * (q_in + s.riv);
             s.riv = s.riv + (q_in - q);
         } else {
@@ -246,8 +255,6 @@ __device__ __forceinline__ R soil_total(const MemberState<R> &s)
 #endif
 }
 
-__device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
-__device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >= 0; }
 
 // ---- pieces of the fast step ---------------------------------------------------------------
 
