@@ -42,6 +42,9 @@ constexpr int kStepUnroll = SMART_STEP_UNROLL;   // unroll factor of the per-ste
 #ifndef SMART_FAST_REGS_F64_LEAN
 #define SMART_FAST_REGS_F64_LEAN 80   // lean budget: 25 warps per SM, a few bytes of spills
 #endif
+#ifndef SMART_SLOW_REGS
+#define SMART_SLOW_REGS 128         // branch-faithful kernels (general, fluxes)
+#endif
 #ifndef SMART_FAST_REGS_F32
 #define SMART_FAST_REGS_F32 72     // fast FP32 kernel: 70 registers used, no spills, 28 warps per SM (sweep 64..96)
 #endif
@@ -926,7 +929,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     // last wave (config C2: 1e5 members are 1.06 waves at 90 registers, 0.88 at 80).
     constexpr int kLeanRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64_LEAN : SMART_FAST_REGS_F32;
     constexpr int kRoomyRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64 : SMART_FAST_REGS_F32;
-    constexpr int kSlowRegs = 128;
+    constexpr int kSlowRegs = SMART_SLOW_REGS;
     Kernel fast_lean, fast_roomy, general, fluxes;
     auto pick = [&](auto block_tag, auto single_tag, auto daily_tag) {
         constexpr int B = decltype(block_tag)::value;
