@@ -260,15 +260,16 @@ __device__ __forceinline__ R soil_total(const MemberState<R> &s)
 
 // Wet hour, soil part (structure.py:360-399): overland split, fill ladder, saturation excess,
 // three leak passes.  ex = rain * T - peva >= 0.  Returns the three merged inflows.
+// hex = (H / Z) * ex, formed by the caller (once per block when the forcing is block-constant).
 template <typename R, int kStride>
 __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R> &p, R D, R omD,
-                                              FastCarry<R> &carry, R ex, R &in_quick, R &in_int, R &in_gw)
+                                              FastCarry<R> &carry, R ex, R hex, R &in_quick, R &in_int, R &in_gw)
 {
     constexpr bool kLeakByDifference = sizeof(R) == 8;
     const R zero = R(0);
     R tot = carry.tot;
     if (!carry.valid) tot = soil_total(s);
-    in_quick = (p.Hz * tot) * ex;                   // :363-364
+    in_quick = hex * tot;                           // :363-364, h' * excess = (H/Z * excess) * total
     const R u0 = in_quick - ex;                     // u = -(excess rain still to place) <= 0
     R u = u0;
     auto fill = [&](int i) {                        // :367-374
@@ -388,8 +389,8 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
     o.q_riv = q;
 
     if (ex_d >= 0.0) {
-        fast_wet_soil<R, kStride>(s, p, kc[1 * kStride], kc[2 * kStride], carry, static_cast<R>(ex_d), in_quick, in_int,
-                                  in_gw);
+        const R ex = static_cast<R>(ex_d);
+        fast_wet_soil<R, kStride>(s, p, kc[1 * kStride], kc[2 * kStride], carry, ex, p.Hz * ex, in_quick, in_int, in_gw);
     } else {
         fast_dry_soil<R>(s, kc[0], static_cast<R>(-ex_d));
         carry.valid = false;
@@ -431,22 +432,25 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
     if (ex_d >= 0.0) {
         const R ex = static_cast<R>(ex_d);
         const R D = kc[1 * kStride], omD = kc[2 * kStride];
+        const R hex = p.Hz * ex;                    // constant over the block
+        const R r_sk = kc[3 * kStride], r_fk = kc[4 * kStride], r_gk = kc[5 * kStride];
+        R sum_riv = R(0);                           // river outflow of the block = r_rk * sum of the store
 #pragma unroll kWetUnroll
         for (int h = 0; h < rep; ++h) {
-            const R q_quick = s.ove * kc[3 * kStride];
-            const R q_int = s.itf * kc[4 * kStride];
-            const R q_gw = s.sgw * kc[5 * kStride];
-            const R q = s.riv * kc[6 * kStride];
-            const R q_in = (q_quick + q_int) + q_gw;
-            s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - q) + q_in;
-            acc += q;
+            // outflows from the OLD storage (:427-447): Q_gw alone (groundwater share), and the river
+            // inflow as one fused dot product r_sk V_quick + r_fk V_int + Q_gw (:254)
+            const R q_gw = s.sgw * r_gk;
+            const R q_in = fma(r_sk, s.ove, fma(r_fk, s.itf, q_gw));
+            sum_riv += s.riv;
             agw += q_gw;
+            s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - s.riv * kc[6 * kStride]) + q_in;
             R in_quick, in_int, in_gw;
-            fast_wet_soil<R, kStride>(s, p, D, omD, carry, ex, in_quick, in_int, in_gw);
-            s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - q_quick) + in_quick;
-            s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - q_int) + in_int;
+            fast_wet_soil<R, kStride>(s, p, D, omD, carry, ex, hex, in_quick, in_int, in_gw);
+            s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - s.ove * r_sk) + in_quick;
+            s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - s.itf * r_fk) + in_int;
             s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
         }
+        acc += sum_riv * kc[6 * kStride];
     } else {
         // Soil over the whole dry block, per member (a member's arithmetic never depends on the
         // other lanes of its warp).  Nothing refills the layers, so each one runs empty at most
