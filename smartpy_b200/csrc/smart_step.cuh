@@ -378,11 +378,10 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
 
     // Outflows leave from the OLD storage (structure.py:427-447, :487), so they and the whole
     // river update do not wait for the soil: issue them first.  SK/SK and GK/GK stores merged.
-    const R q_quick = s.ove * kc[3 * kStride];
-    const R q_int = s.itf * kc[4 * kStride];
+    const R r_sk = kc[3 * kStride], r_fk = kc[4 * kStride];
     const R q_gw = s.sgw * kc[5 * kStride];
     const R q = s.riv * kc[6 * kStride];
-    const R q_in = (q_quick + q_int) + q_gw;            // :254
+    const R q_in = fma(r_sk, s.ove, fma(r_fk, s.itf, q_gw));            // :254 as one fused dot product
     s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - q) + q_in;   // :487-498, cap cannot fire
     o.q_gw = q_gw;
     o.q_all = q_in;
@@ -399,8 +398,8 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
     // binary64 advances a store with one FMA, V' = V * (1 - dt/k) + inflow; in binary32 the
     // rounding of (1 - dt/k) would bias the recession constant by up to 1e-4, so the two-step
     // form V' = (V - Q) + inflow is kept there.
-    s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - q_quick) + in_quick;
-    s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - q_int) + in_int;
+    s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - s.ove * r_sk) + in_quick;
+    s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - s.itf * r_fk) + in_int;
     s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
 }
 
