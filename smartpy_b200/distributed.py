@@ -21,6 +21,12 @@ def rank_world():
     return 0, 1
 
 
+def barrier():
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+
+
 def shard_bounds(n_rows, rank, world):
     """Contiguous, balanced row block of `rank`: sizes differ by at most one, earlier ranks larger."""
     base, extra = divmod(int(n_rows), int(world))

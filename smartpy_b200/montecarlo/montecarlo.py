@@ -208,9 +208,11 @@ class MonteCarlo(object):
         compression: for 'csv' a bool (gzip the database); for 'netcdf' a bool or the zlib
         complevel 1-9 (True = 6); None = no compression (montecarlo.py:132-177).
         """
-        self._init_db()
         n_obj = len(self.obj_fn_names)
         rank, world = dist_utils.rank_world() if self.p else (0, 1)
+        writer = rank == 0          # with several ranks only the first one owns the database file
+        if writer:
+            self._init_db()
         lo, hi = dist_utils.shard_bounds(self.sample_params.shape[0], rank, world)
         engine = self.model.get_engine(report='summary', gw_constraint=self.constraints['gw'],
                                        precision=self.precision)
@@ -230,10 +232,14 @@ class MonteCarlo(object):
         if world > 1:
             scores, gw = dist_utils.all_gather_rows(scores, gw, self.sample_params.shape[0])
         self.results = {'scores': scores[:, :n_obj], 'gw': gw}
-        if not self.save_sim or world > 1:
-            if rank == 0 or not self.p:
+        if writer:
+            if not self.save_sim or world > 1:
                 self._save_block(0, scores[:, :n_obj].cpu().numpy(), self.sample_params, None)
-        self.database.close()
+            self.database.close()
+        if world > 1:
+            dist_utils.barrier()
+        if not writer:
+            return
 
         # if compression argument given, the file created will be compressed
         if self.out_format == 'netcdf':

@@ -7,7 +7,7 @@ CUDA kernel (one member per ``simulate`` call; ``simulate_batch`` for many).
 conditions guess, the warm-up run and the main run all happen inside one kernel launch.
 There is no CPU path: without the built library or without a GPU it raises.
 """
-from os import path, makedirs, sep
+from os import makedirs, sep
 
 import numpy as np
 
@@ -33,8 +33,7 @@ class SMART(object):
         self.root_f = root
         self.in_f = sep.join([self.root_f, 'in', self.catchment, sep])
         self.out_f = sep.join([self.root_f, 'out', self.catchment, sep])
-        if not path.exists(self.out_f):
-            makedirs(self.out_f)
+        makedirs(self.out_f, exist_ok=True)      # (exist_ok: several ranks may get here together)
         # temporal information
         self.start = start
         self.end = end
