@@ -171,6 +171,47 @@ int smart_allsteps_host(double area_m2, double delta_sec, int64_t length_simu,
  */
 int smart_fma_peak_probe(int precision, int blocks, int threads, int64_t iters, double *out, void *stream);
 
+/*
+ * Conditioning of a scored sample on the device.  `scores` is the
+ * [n_rows][ld] table of doubles a batch run wrote (ld >= the columns used), device memory.
+ * A condition keeps the rows whose `column` value is == lo (EQUAL), >= lo (MIN), <= lo (MAX),
+ * in [lo, hi] (INSIDE) or "<= lo and >= hi" (OUTSIDE, the reference's literal rule); NaN fails
+ * every comparison.  Replaces the numpy masks of smartpy/montecarlo/glue.py:246-289 and the
+ * mask + full argsort of smartpy/montecarlo/best.py:243-287.
+ */
+#define SMART_MAX_CONDITIONS 8
+enum { SMART_COND_EQUAL = 0, SMART_COND_MIN = 1, SMART_COND_MAX = 2, SMART_COND_INSIDE = 3, SMART_COND_OUTSIDE = 4 };
+
+typedef struct smart_condition {
+    int32_t column;
+    int32_t kind;
+    double lo;
+    double hi;
+} smart_condition;
+
+/* bytes of device scratch both calls below need for n_rows rows and (smart_best_rows) k winners */
+size_t smart_condition_workspace_bytes(int64_t n_rows, int64_t k);
+
+/*
+ * GLUE: rows_out[0..*count_out) = ascending indices of the rows passing all conditions
+ * (rows_out: device, room for n_rows; count_out: device, one int64).  `conds` is HOST memory
+ * (copied into the launch); stream-ordered, no allocation, no synchronisation.
+ */
+int smart_condition_rows(const double *scores, int64_t n_rows, int32_t ld, const smart_condition *conds,
+                         int32_t n_conds, int64_t *rows_out, int64_t *count_out, void *workspace, void *stream);
+
+/*
+ * Best: rows_out[0..k) = the rows holding the k largest values of `target_column` among the
+ * rows passing the conditions, in ascending order of (value, row) -- the best set last, ties
+ * resolved like numpy.argsort(kind='stable')[-k:], NaN counted as the largest value like numpy
+ * does.  *kept_out (device int64, may be NULL) = rows passing the conditions; when it is < k
+ * the output is meaningless and the caller raises the reference's "restrained sample size"
+ * exception (best.py:284-285).  Radix select + sort of the k winners only.
+ */
+int smart_best_rows(const double *scores, int64_t n_rows, int32_t ld, int32_t target_column,
+                    const smart_condition *conds, int32_t n_conds, int64_t k, int64_t *rows_out,
+                    int64_t *kept_out, void *workspace, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,7 +34,17 @@ SYMBOLS = (
     "smart_obs_stats", "smart_batch_run_f64", "smart_batch_run_f32", "smart_score_discharge",
     "smart_disaggregate", "smart_expand", "smart_stamp", "smart_batch_run_host",
     "smart_allsteps_host", "smart_fma_peak_probe",
+    "smart_condition_workspace_bytes", "smart_condition_rows", "smart_best_rows",
 )
+
+MAX_CONDITIONS = 8
+COND_KINDS = {'equal': 0, 'min': 1, 'max': 2, 'inside': 3, 'outside': 4}
+
+
+class Condition(ctypes.Structure):
+    """Mirror of ``smart_condition`` (include/smart_b200.h)."""
+    _fields_ = [("column", ctypes.c_int32), ("kind", ctypes.c_int32), ("lo", ctypes.c_double),
+                ("hi", ctypes.c_double)]
 
 
 class BatchDesc(ctypes.Structure):
@@ -131,6 +141,16 @@ def load():
     lib.smart_fma_peak_probe.restype = ctypes.c_int
     lib.smart_fma_peak_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int64,
                                          ctypes.c_void_p, ctypes.c_void_p]
+    lib.smart_condition_workspace_bytes.restype = ctypes.c_size_t
+    lib.smart_condition_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64]
+    pcond = ctypes.POINTER(Condition)
+    lib.smart_condition_rows.restype = ctypes.c_int
+    lib.smart_condition_rows.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, pcond, ctypes.c_int32,
+                                         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.smart_best_rows.restype = ctypes.c_int
+    lib.smart_best_rows.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, pcond,
+                                    ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                    ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
     return lib
 

@@ -1000,6 +1000,9 @@ struct DevBuf {
 
 }  // namespace
 
+// error channel shared with smart_select.cu
+int smart_internal_fail(int code, const char *msg) { return fail(code, msg); }
+
 // =================================================================== C ABI
 extern "C" {
 

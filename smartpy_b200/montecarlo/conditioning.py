@@ -2,12 +2,18 @@
 
 The reference conditions a sample after a round trip through a float32 text/NetCDF file
 (``montecarlo.py:233-262``) with numpy masks and a full ``argsort`` (``glue.py:246-289``,
-``best.py:243-287``).  With the scores already on the GPU (``MonteCarlo.results``) the same
-selections are a handful of tensor operations; the functions below work on any torch tensor
-(CUDA or CPU) and follow the reference's rules, including its tie order (ascending sort, best
-last) and its literal 'outside' rule.
+``best.py:243-287``).  With the scores already in HBM (``MonteCarlo.results``) the same
+selections are two calls into the CUDA library: ``smart_condition_rows`` (predicate mask +
+ordered compaction) and ``smart_best_rows`` (radix select of the k best + sort of those k only),
+``include/smart_b200.h``.  They follow the reference's rules, including its order (ascending,
+best last), numpy's NaN-sorts-last rule and the literal 'outside' rule.  CUDA tensors only:
+the file-based GLUE/Best classes keep the numpy rules (``montecarlo.condition_mask``).
 """
+import ctypes
+
 import numpy as np
+
+from .. import _native
 
 
 def _torch():
@@ -15,45 +21,71 @@ def _torch():
     return torch
 
 
-def condition_mask_tensor(scores, columns, conditions_val, conditions_typ):
-    """Boolean tensor over the rows of scores[N, k']: AND of the (kind, values) conditions on the
-    given columns.  Same kinds and error messages as glue.py:246-286."""
-    torch = _torch()
-    mask = torch.ones((scores.shape[0],), dtype=torch.bool, device=scores.device)
-    for col, values, kind in zip(columns, conditions_val, conditions_typ):
-        x = scores[:, col]
+def _conditions(columns, conditions_val, conditions_typ):
+    """(kind, values) conditions -> ctypes array of smart_condition; same checks and messages as
+    glue.py:246-286."""
+    if len(columns) > _native.MAX_CONDITIONS:
+        raise Exception("At most {} conditions can be combined.".format(_native.MAX_CONDITIONS))
+    conds = (_native.Condition * max(1, len(columns)))()
+    for i, (col, values, kind) in enumerate(zip(columns, conditions_val, conditions_typ)):
         if kind in ('equal', 'min', 'max'):
             if len(values) != 1:
                 raise Exception("The tuple for \"{}\" condition does not contain one and only one "
                                 "element.".format(kind))
-            sel = (x == values[0]) if kind == 'equal' else (x >= values[0]) if kind == 'min' else (x <= values[0])
+            lo, hi = float(values[0]), 0.0
         elif kind in ('inside', 'outside'):
             if len(values) != 2:
                 raise Exception("The tuple for \"{}\" condition does not contain two and only two "
                                 "elements.".format(kind))
             if not values[1] > values[0]:
                 raise Exception("The two elements of the tuple for \"{}\" are inconsistent.".format(kind))
-            if kind == 'inside':
-                sel = (x >= values[0]) & (x <= values[1])
-            else:
-                sel = (x <= values[0]) & (x >= values[1])
+            lo, hi = float(values[0]), float(values[1])
         else:
             raise Exception("The type of threshold \"{}\" is not in the database.".format(kind))
-        mask &= sel
-    return mask
+        conds[i] = _native.Condition(int(col), _native.COND_KINDS[kind], lo, hi)
+    return conds
+
+
+def _score_table(scores):
+    """(tensor, rows, leading dimension) of a float64 CUDA score table whose rows are unit-stride
+    (a column slice of the kernel's [N, 8] output is fine)."""
+    torch = _torch()
+    if not (torch.is_tensor(scores) and scores.is_cuda):
+        raise RuntimeError("device conditioning needs the CUDA score table of a batch run "
+                           "(smartpy_b200 has no CPU path; use GLUE/Best on the sample database instead)")
+    if scores.dim() != 2 or scores.dtype != torch.float64:
+        raise ValueError("scores must be a [N, k] float64 tensor")
+    if scores.shape[0] > 0 and (scores.stride(1) != 1 or scores.stride(0) < scores.shape[1]):
+        scores = scores.contiguous()
+    ld = scores.stride(0) if scores.shape[0] > 1 else max(scores.shape[1], 1)
+    return scores, scores.shape[0], ld
+
+
+def _rows_where(scores, columns, conditions_val, conditions_typ):
+    torch = _torch()
+    conds = _conditions(columns, conditions_val, conditions_typ)
+    scores, n, ld = _score_table(scores)
+    lib = _native.load()
+    with torch.cuda.device(scores.device):
+        rows = torch.empty((n,), dtype=torch.int64, device=scores.device)
+        count = torch.zeros((1,), dtype=torch.int64, device=scores.device)
+        work = torch.empty((max(1, lib.smart_condition_workspace_bytes(n, 0)),), dtype=torch.uint8,
+                           device=scores.device)
+        _native.check(lib.smart_condition_rows(
+            scores.data_ptr(), n, ld, conds, len(columns), rows.data_ptr(), count.data_ptr(),
+            work.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return rows[:int(count.item())]
 
 
 def behavioural_rows(scores, obj_fn_names, conditioning):
     """Row indices (ascending) of the behavioural sets -- GLUE (glue.py:222-289)."""
-    torch = _torch()
     try:
         columns = [obj_fn_names.index(fn) for fn in conditioning]
     except ValueError:
         raise Exception("One of the names of objective functions for conditioning in GLUE is not recognised."
                         "Please check for typos and case sensitive issues.")
-    mask = condition_mask_tensor(scores, columns, [conditioning[fn][1] for fn in conditioning],
-                                 [conditioning[fn][0] for fn in conditioning])
-    return torch.nonzero(mask, as_tuple=False)[:, 0]
+    return _rows_where(scores, columns, [conditioning[fn][1] for fn in conditioning],
+                       [conditioning[fn][0] for fn in conditioning])
 
 
 def best_rows(scores, obj_fn_names, target, nb_best, constraining=None):
@@ -65,8 +97,7 @@ def best_rows(scores, obj_fn_names, target, nb_best, constraining=None):
     except ValueError:
         raise Exception("The objective function {} for conditioning in Best is not recognised."
                         "Please check for typos and case sensitive issues.".format(target))
-    n = scores.shape[0]
-    if nb_best > n:
+    if nb_best > scores.shape[0]:
         raise Exception('The number of best models requested is higher than the sample size.')
     constraining = constraining or {}
     try:
@@ -74,16 +105,24 @@ def best_rows(scores, obj_fn_names, target, nb_best, constraining=None):
     except ValueError:
         raise Exception("One of the names of constraints in Best is not recognised."
                         "Please check for typos and case sensitive issues.")
-    mask = condition_mask_tensor(scores, columns, [constraining[fn][1] for fn in constraining],
-                                 [constraining[fn][0] for fn in constraining])
-    kept = torch.nonzero(mask, as_tuple=False)[:, 0]
-    if nb_best > kept.numel():
-        raise Exception('The number of best models requested is higher than the restrained sample size.')
-    values = scores[kept, t_col]
-    # top-k instead of a full sort; re-sorted ascending so that the best set comes last
-    top = torch.topk(values, nb_best, largest=True, sorted=True)
-    order = torch.flip(top.indices, dims=[0])
-    return kept[order]
+    conds = _conditions(columns, [constraining[fn][1] for fn in constraining],
+                        [constraining[fn][0] for fn in constraining])
+    scores, n, ld = _score_table(scores)
+    nb_best = int(nb_best)
+    if nb_best < 1:
+        return torch.empty((0,), dtype=torch.int64, device=scores.device)
+    lib = _native.load()
+    with torch.cuda.device(scores.device):
+        rows = torch.empty((nb_best,), dtype=torch.int64, device=scores.device)
+        kept = torch.zeros((1,), dtype=torch.int64, device=scores.device)
+        work = torch.empty((lib.smart_condition_workspace_bytes(n, nb_best),), dtype=torch.uint8,
+                           device=scores.device)
+        _native.check(lib.smart_best_rows(
+            scores.data_ptr(), n, ld, t_col, conds, len(columns), nb_best, rows.data_ptr(), kept.data_ptr(),
+            work.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        if nb_best > int(kept.item()):
+            raise Exception('The number of best models requested is higher than the restrained sample size.')
+    return rows
 
 
 def latin_hypercube_device(sample_size, bounds, device=None, generator=None):

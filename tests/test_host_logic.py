@@ -284,29 +284,25 @@ def test_descriptor_layout_matches_header(tmp_path):
         assert int(out[f]) == getattr(_native.BatchDesc, f).offset, f
 
 
-def test_device_conditioning_matches_reference_rules():
-    """conditioning.py on CPU tensors against the numpy rules kept in GLUE/Best."""
+def test_device_conditioning_argument_checks():
+    """conditioning.py: the reference's error messages are raised before any device work, and a
+    CPU tensor is refused (there is no CPU path)."""
     import torch
     from smartpy_b200.montecarlo import conditioning
-    from smartpy_b200.montecarlo.glue import GLUE
-    from smartpy_b200.montecarlo.best import Best
-    rng = np.random.RandomState(3)
     names = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
-    scores = rng.randn(500, 8)
-    scores[:, 7] = rng.rand(500) > 0.5
-    params = rng.rand(500, 10)
-    t = torch.from_numpy(scores)
-    cond = {'NSE': ('min', (0.2,)), 'PBias': ('inside', (-1.0, 1.0)), 'GW': ('equal', (1.0,))}
-    rows = conditioning.behavioural_rows(t, names, cond).numpy()
-    ref = GLUE._get_behavioural_sets(params, scores[:, [0, 5, 7]], [cond[k][1] for k in cond], [cond[k][0] for k in cond])
-    assert np.array_equal(params[rows], ref)
-    rows = conditioning.best_rows(t, names, 'KGE', 7, {'RMSE': ('max', (0.5,))}).numpy()
-    ref = Best._get_best_sets(params, scores[:, [6]], [(0.5,)], ['max'], scores[:, [1]], 7)
-    assert np.array_equal(params[rows], ref)
-    with pytest.raises(Exception, match="restrained sample size"):
-        conditioning.best_rows(t, names, 'KGE', 400, {'RMSE': ('max', (-5.0,))})
+    t = torch.zeros((20, 8), dtype=torch.float64)
     with pytest.raises(Exception, match="not recognised"):
         conditioning.best_rows(t, names, 'XYZ', 1)
+    with pytest.raises(Exception, match="higher than the sample size"):
+        conditioning.best_rows(t, names, 'NSE', 21)
+    with pytest.raises(Exception, match="one and only one"):
+        conditioning.behavioural_rows(t, names, {'NSE': ('min', (0.1, 0.2))})
+    with pytest.raises(Exception, match="inconsistent"):
+        conditioning.behavioural_rows(t, names, {'NSE': ('inside', (0.3, 0.2))})
+    with pytest.raises(Exception, match="not in the database"):
+        conditioning.behavioural_rows(t, names, {'NSE': ('about', (0.3,))})
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        conditioning.behavioural_rows(t, names, {'NSE': ('min', (0.1,))})
 
 
 def test_device_lhs_is_stratified():
