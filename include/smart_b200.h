@@ -212,6 +212,18 @@ int smart_best_rows(const double *scores, int64_t n_rows, int32_t ld, int32_t ta
                     const smart_condition *conds, int32_t n_conds, int64_t k, int64_t *rows_out,
                     int64_t *kept_out, void *workspace, void *stream);
 
+/*
+ * Latin Hypercube sample on the device (the construction of
+ * smartpy/montecarlo/lhs.py:133-167 with the host permutation replaced by a keyed bijection, so
+ * any row range can be generated on its own: a rank writes rows [row_first, row_first + n_rows)
+ * of the [n_total][n_params] sample into out[n_rows][n_params] (device) and the union over the
+ * ranks is ONE stratified sample).  `bounds` is HOST memory, [n_params][2] = (lower, upper).
+ * Not the reference's random stream; the algorithm is spelled out in csrc/smart_sample.cu.
+ */
+#define SMART_LHS_MAX_PARAMS 16
+int smart_lhs_rows(uint64_t seed, int64_t n_total, int64_t row_first, int64_t n_rows, int32_t n_params,
+                   const double *bounds, double *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

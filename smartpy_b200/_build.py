@@ -4,7 +4,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-SOURCES = [os.path.join(_HERE, "csrc", "smart_kernels.cu"), os.path.join(_HERE, "csrc", "smart_select.cu")]
+SOURCES = [os.path.join(_HERE, "csrc", "smart_kernels.cu"), os.path.join(_HERE, "csrc", "smart_select.cu"),
+           os.path.join(_HERE, "csrc", "smart_sample.cu")]
 HEADERS = [os.path.join(_HERE, "csrc", "smart_step.cuh"), os.path.join(ROOT, "include", "smart_b200.h")]
 LIB_PATH = os.path.join(_HERE, "libsmart_b200.so")
 

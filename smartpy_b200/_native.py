@@ -35,6 +35,7 @@ SYMBOLS = (
     "smart_disaggregate", "smart_expand", "smart_stamp", "smart_batch_run_host",
     "smart_allsteps_host", "smart_fma_peak_probe",
     "smart_condition_workspace_bytes", "smart_condition_rows", "smart_best_rows",
+    "smart_lhs_rows",
 )
 
 MAX_CONDITIONS = 8
@@ -151,6 +152,9 @@ def load():
     lib.smart_best_rows.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, pcond,
                                     ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                     ctypes.c_void_p, ctypes.c_void_p]
+    lib.smart_lhs_rows.restype = ctypes.c_int
+    lib.smart_lhs_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
     return lib
 

@@ -125,18 +125,26 @@ def best_rows(scores, obj_fn_names, target, nb_best, constraining=None):
     return rows
 
 
-def latin_hypercube_device(sample_size, bounds, device=None, generator=None):
-    """Latin Hypercube sample [sample_size, n_params] built on the device:
-    one stratum per row and column, strata visited in the order of a random permutation obtained
-    by sorting Philox random keys, jitter uniform within the stratum -- the construction of
-    lhs.py:133-167 without the host round trip.  Not the reference's random stream (use
-    montecarlo.lhs.latin_hypercube for that); the stratification property is what is kept."""
+def latin_hypercube_device(sample_size, bounds, device=None, seed=0, row_first=0, n_rows=None):
+    """Rows [row_first, row_first + n_rows) of a Latin Hypercube sample [sample_size, n_params],
+    generated on the device by ``smart_lhs_rows``: one stratum per row and
+    column as in lhs.py:133-167, the strata order given by a keyed bijection instead of a host
+    permutation, so each rank of a sharded run generates only its own rows and the union is one
+    stratified sample.  Not the reference's random stream (montecarlo.lhs.latin_hypercube keeps
+    that one); the stratification property is what is kept.  Returns a CUDA float64 tensor."""
     torch = _torch()
-    bounds_t = torch.as_tensor(np.asarray(bounds, dtype=np.float64), device=device)
-    n_params = bounds_t.shape[0]
-    keys = torch.rand((n_params, sample_size), dtype=torch.float64, device=device, generator=generator)
-    strata = torch.argsort(keys, dim=1).to(torch.float64)
-    jitter = torch.rand((n_params, sample_size), dtype=torch.float64, device=device, generator=generator)
-    quantiles = (strata + jitter) / sample_size
-    lower, width = bounds_t[:, 0:1], (bounds_t[:, 1:2] - bounds_t[:, 0:1])
-    return (quantiles * width + lower).t().contiguous()
+    bounds = np.ascontiguousarray(bounds, dtype=np.float64)
+    if bounds.ndim != 2 or bounds.shape[1] != 2:
+        raise ValueError("bounds must be [n_params, 2]")
+    n_rows = int(sample_size) - int(row_first) if n_rows is None else int(n_rows)
+    device = torch.device('cuda' if device is None else device)
+    if device.type != 'cuda':
+        raise RuntimeError("latin_hypercube_device runs on a CUDA device (smartpy_b200 has no CPU path; "
+                           "montecarlo.lhs.latin_hypercube is the host sampler)")
+    lib = _native.load()
+    with torch.cuda.device(device):
+        out = torch.empty((max(n_rows, 0), bounds.shape[0]), dtype=torch.float64, device=device)
+        _native.check(lib.smart_lhs_rows(int(seed) & 0xFFFFFFFFFFFFFFFF, int(sample_size), int(row_first), n_rows,
+                                         bounds.shape[0], bounds.ctypes.data, out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+    return out

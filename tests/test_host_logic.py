@@ -303,17 +303,3 @@ def test_device_conditioning_argument_checks():
         conditioning.behavioural_rows(t, names, {'NSE': ('about', (0.3,))})
     with pytest.raises(RuntimeError, match="no CPU path"):
         conditioning.behavioural_rows(t, names, {'NSE': ('min', (0.1,))})
-
-
-def test_device_lhs_is_stratified():
-    import torch
-    from smartpy_b200.montecarlo.conditioning import latin_hypercube_device
-    from smartpy_b200.parameters import Parameters
-    p = Parameters()
-    bounds = [p.ranges[n] for n in p.names]
-    g = torch.Generator().manual_seed(5)
-    sample = latin_hypercube_device(2000, bounds, generator=g).numpy()
-    assert sample.shape == (2000, 10)
-    for k, (lo, hi) in enumerate(bounds):
-        strata = np.floor((sample[:, k] - lo) / (hi - lo) * 2000).astype(int)
-        assert sorted(strata.tolist()) == list(range(2000))
