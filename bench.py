@@ -54,7 +54,7 @@ I_DRY, I_WET = 65.5, 135.5
 KERNELS_PER_RUN = 2
 
 # members each host worker simulates per CPU-arm step (C oracle: ~26 ms per 96k-step member)
-CPU_MEMBERS_PER_WORKER = 24
+CPU_MEMBERS_PER_WORKER = 96      # a bounded sample: a few seconds of wall time per CPU-arm step on 16 cores
 
 
 # ---------------------------------------------------------------------------------------- workloads

@@ -18,6 +18,11 @@ ncu --set full --clock-control none --import-source on -k regex:smart_batch_kern
 python bench.py --workload c3 --steps 2 --no-cpu-baseline > $O/bench_${R}_c3.json
 python bench.py --workload c5 --steps 3 --no-cpu-baseline > $O/bench_${R}_c5.json
 python bench.py --workload c4a --steps 2 --no-cpu-baseline > $O/bench_${R}_c4a.json
+python bench.py --workload c4b --steps 2 --no-cpu-baseline > $O/bench_${R}_c4b.json
+# FP32 mode: the same full capture of its kernel
+ncu --set full --clock-control none --import-source on -k regex:smart_batch_kernel -s 6 -c 1 -o $O/prof_${R}_c5 \
+    python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e > $O/ncu_full_${R}_c5.log 2>&1
+python tools/bench_conditioning.py 10000000 > $O/conditioning_bench_$R.json
 python bench.py --flags 65536 --steps 3 --no-cpu-baseline > $O/bench_${R}_c2_perstep.json
 python bench.py --flags 1 --steps 3 --no-cpu-baseline > $O/bench_${R}_c2_general.json
 python tools/parity_report.py > $O/parity_report_$R.txt
