@@ -450,7 +450,12 @@ def main():
         "executed": ({"fp64_warp_inst_per_warp_step": ncu["fp64_inst_per_step"],
                       "frac_of_peak": per_gpu * ncu["fp64_inst_per_step"] / peak_fma,
                       "ncu_fp64_pipe_active_pct": ncu.get("fp64_pipe_active_pct"),
-                      "source": ncu.get("source")} if ncu.get("fp64_inst_per_step") else None),
+                      "source": ncu.get("source")} if ncu.get("fp64_inst_per_step") else
+                     {"fp32_warp_inst_per_warp_step": ncu["fp32_inst_per_step"],
+                      "frac_of_peak": per_gpu * ncu["fp32_inst_per_step"] / peak_fma,
+                      "ncu_fma_pipe_active_pct": ncu.get("fma_pipe_active_pct"),
+                      "ncu_issue_active_pct": ncu.get("issue_active_pct"),
+                      "source": ncu.get("source")} if ncu.get("fp32_inst_per_step") else None),
         "hbm": {"achieved_gbs": hbm_bytes_per_step / (ms_per_step * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": hbm_bytes_per_step / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
@@ -475,7 +480,8 @@ def main():
         line["e2e"] = {"value": total_steps / (ms_e2e * 1e-3), "unit": METRIC,
                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "ms_per_step": ms_e2e / args.steps,
-                       "api": "BatchEngine.run -> smart_batch_run_f64 (C ABI), pinned host params in, host scores out"}
+                       "api": "BatchEngine.run -> smart_batch_run_{} (C ABI), pinned host params in, host scores out".format(
+                           precision)}
     if world == 1 and not args.no_cpu_baseline:
         pool, cores = make_pool(w)
         v, secs, sample = cpu_throughput(w, pool, cores, per_worker=CPU_MEMBERS_PER_WORKER)
