@@ -56,3 +56,28 @@ def all_gather_rows(scores, gw, n_rows):
         parts.append(gathered[r, :hi - lo])
     full = torch.cat(parts)
     return full[:, :-1].contiguous(), full[:, -1].contiguous()
+
+
+def all_gather_best(best_score, best_index, first_row, sign=1):
+    """Best-member-only runs (no score table wanted): every rank hands in the (score, local row)
+    pair its kernel selected (``BatchEngine.run(best=...)``); ONE all-gather of world pairs, then
+    the arg-max (sign > 0) or arg-min over them on every rank.  Returns tensors (score [1] float64,
+    global row [1] int64) on the input's device.  A NaN score never wins against a number; ties
+    go to the lowest global row."""
+    import torch
+    dist = _dist()
+    rank, world = rank_world()
+    score = best_score.reshape(1).to(torch.float64)
+    row = best_index.reshape(1).to(torch.int64) + int(first_row)
+    if world == 1:
+        return score, row
+    pair = torch.stack([score[0], row[0].to(torch.float64)])       # rows < 2^53: exact in float64
+    flat = torch.empty((world * 2,), dtype=torch.float64, device=pair.device)
+    dist.all_gather_into_tensor(flat, pair.contiguous())
+    pairs = flat.view(world, 2)
+    key = pairs[:, 0] if sign > 0 else -pairs[:, 0]
+    key = torch.where(torch.isnan(key), torch.full_like(key, float('-inf')), key)
+    winners = key == key.max()
+    rows = torch.where(winners, pairs[:, 1], torch.full_like(pairs[:, 1], float('inf')))
+    who = torch.argmin(rows)
+    return pairs[who, 0].reshape(1), pairs[who, 1].to(torch.int64).reshape(1)

@@ -40,3 +40,27 @@ def test_shard_and_all_gather_world2(tmp_path):
         for rank in range(2):
             assert np.array_equal(np.load(tmp_path / ("scores_%d.npy" % rank)), expect)
             assert np.array_equal(np.load(tmp_path / ("gw_%d.npy" % rank)), -np.arange(n_rows, dtype=np.float64))
+
+
+def _best_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from smartpy_b200 import distributed as du
+    # (local best score, local row) per rank and case; first_row = 100 * rank
+    cases = [((0.3, 4), (0.7, 2)), ((0.7, 9), (0.7, 1)), ((float('nan'), 0), (-5.0, 3)), ((0.1, 1), (0.2, 2))]
+    got = []
+    for k, case in enumerate(cases):
+        score, row = case[rank]
+        sign = -1 if k == 3 else 1
+        s, r = du.all_gather_best(torch.tensor([score], dtype=torch.float64), torch.tensor([row]), 100 * rank, sign)
+        got.append((float(s[0]), int(r[0])))
+    np.save(os.path.join(out_dir, "best_%d.npy" % rank), np.array(got))
+    dist.destroy_process_group()
+
+
+def test_best_member_pairs_world2(tmp_path):
+    mp.spawn(_best_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    expect = np.array([(0.7, 102), (0.7, 9), (-5.0, 103), (0.1, 1)])
+    for rank in range(2):
+        assert np.array_equal(np.load(tmp_path / ("best_%d.npy" % rank)), expect)

@@ -33,6 +33,13 @@ def _worker(rank, world, port, root, out_dir):
     setup.db_file = os.path.join(out_dir, "sharded.lhs")
     setup.run()
     np.save(os.path.join(out_dir, "scores_%d.npy" % rank), setup.results['scores'].cpu().numpy())
+    # best-member-only run: no score table, one all-gather of `world` (score, row) pairs
+    from smartpy_b200 import distributed as du
+    lo, hi = du.shard_bounds(setup.sample_params.shape[0], rank, world)
+    engine = setup.model.get_engine(report='summary', gw_constraint=setup.constraints['gw'])
+    res = engine.run(setup.sample_params[lo:hi], discharge=False, scores=False, gw=False, best=('KGE', 1))
+    score, row = du.all_gather_best(res['best'][0], res['best'][1], lo, 1)
+    np.save(os.path.join(out_dir, "best_%d.npy" % rank), np.array([float(score[0]), float(row[0])]))
     dist.destroy_process_group()
 
 
@@ -53,3 +60,7 @@ def test_lhs_run_sharded_over_two_gpus(catchment_dir, tmp_path):  # noqa: F811
         assert np.array_equal(got, ref, equal_nan=True)
     with open(single.db_file) as a, open(tmp_path / "sharded.lhs") as b:
         assert a.read() == b.read()
+    kge = ref[:, 1]
+    for rank in range(2):
+        score, row = np.load(tmp_path / ("best_%d.npy" % rank))
+        assert int(row) == int(np.nanargmax(kge)) and score == kge[int(row)]
