@@ -410,6 +410,83 @@ __device__ __forceinline__ void finish_scores(const double *st, double A, double
     sc[6] = sqrt(E / n);                                      // RMSE
 }
 
+// Scores (montecarlo.py:193-209) and groundwater share of one member to global memory.  `acc` is
+// the member's column of the shared-memory accumulators (slot k at acc[k * kStride]).  Returns the
+// member's key for the best-member selection (-inf when it cannot win).
+template <int kStride>
+__device__ __forceinline__ double write_member_results(const KArgs &a, const double *acc, long long m, bool active, int c,
+                                                       double gw)
+{
+    double target = -CUDART_INF;
+    if (a.obs != nullptr) {
+        const double *st = a.obs_stats + c * SMART_OBS_STATS;
+        double sc[SMART_N_SCORES];
+        finish_scores(st, acc[0 * kStride], acc[1 * kStride], acc[2 * kStride], acc[3 * kStride], sc);
+        const bool gw_on = a.gw_constraint == a.gw_constraint && a.gw_constraint != 0.0;
+        sc[7] = gw_on ? ((a.gw_constraint - 0.1 <= gw && gw <= a.gw_constraint + 0.1) ? 1.0 : 0.0)
+                      : CUDART_NAN;                               // objfunctions.py:20-24
+        if (a.scores != nullptr && active) {
+#pragma unroll
+            for (int k = 0; k < SMART_N_SCORES; ++k) a.scores[m * SMART_N_SCORES + k] = sc[k];
+        }
+        if (a.best_sign != 0 && active) {
+            double t = sc[0];
+#pragma unroll
+            for (int k = 1; k < SMART_N_SCORES; ++k) t = (a.best_col == k) ? sc[k] : t;
+            t = a.best_sign > 0 ? t : -t;
+            target = (t == t) ? t : -CUDART_INF;
+        }
+    }
+    if (a.gw != nullptr && active) a.gw[m] = gw;
+    return target;
+}
+
+// Arg-max of (target, idx) over the CTA with warp shuffles; ties go to the lower member index.
+// `scratch` = the accumulator slots, free to reuse once every thread has finished its scores.
+template <int kStride>
+__device__ __forceinline__ void cta_best(const KArgs &a, double *scratch, double target, long long idx)
+{
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ot = __shfl_xor_sync(0xffffffffu, target, off);
+        const long long oi = __shfl_xor_sync(0xffffffffu, idx, off);
+        if (ot > target || (ot == target && oi < idx)) {
+            target = ot;
+            idx = oi;
+        }
+    }
+    __syncthreads();
+    double *s_t = scratch;
+    long long *s_idx = reinterpret_cast<long long *>(scratch + kStride);
+    if ((tid & 31) == 0) {
+        s_t[tid >> 5] = target;
+        s_idx[tid >> 5] = idx;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < static_cast<int>(blockDim.x) / 32; ++w) {
+            const double ot = s_t[w];
+            const long long oi = s_idx[w];
+            if (ot > target || (ot == target && oi < idx)) {
+                target = ot;
+                idx = oi;
+            }
+        }
+        a.blk_best_score[blockIdx.x] = target;
+        a.blk_best_index[blockIdx.x] = idx;
+    }
+}
+
+// The merged ("fast") form is exact only when no clamp, cap or leak predicate can fire:
+// every routing constant >= dt, inflows >= 0 (0 <= D <= 1, 0 <= H < 1), s' < 1.
+__device__ __forceinline__ bool fast_form_ok(const double *par, double dt)
+{
+    return par[6] * 3600.0 >= dt && par[7] * 3600.0 >= dt && par[8] * 3600.0 >= dt && par[9] * 3600.0 >= dt &&
+           par[4] >= 0.0 && par[4] <= 0.5 && par[5] > 0.0 && par[3] >= 0.0 && par[3] <= 1.0 && par[2] >= 0.0 &&
+           par[2] <= 0.99 && par[0] > 0.0;
+}
+
 template <typename R, int kVariant, int BLOCK, bool kSingle, bool kDaily>
 __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
                                            long long m, bool active, int c, int col, int c_base, double area)
@@ -508,28 +585,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
     run_timeline<R, kVariant, BLOCK, kSingle, kDaily>(a, s, p, fp_, sm, m, active, c, col, c_base, area, gw, o);
 
     // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
-    double target = -CUDART_INF;
-    if (a.obs != nullptr) {
-        const double *st = a.obs_stats + c * SMART_OBS_STATS;
-        double sc[SMART_N_SCORES];
-        finish_scores(st, sm.acc[0 * BLOCK + tid], sm.acc[1 * BLOCK + tid], sm.acc[2 * BLOCK + tid],
-                      sm.acc[3 * BLOCK + tid], sc);
-        const bool gw_on = a.gw_constraint == a.gw_constraint && a.gw_constraint != 0.0;
-        sc[7] = gw_on ? ((a.gw_constraint - 0.1 <= gw && gw <= a.gw_constraint + 0.1) ? 1.0 : 0.0)
-                      : CUDART_NAN;                               // objfunctions.py:20-24
-        if (a.scores != nullptr && active) {
-#pragma unroll
-            for (int k = 0; k < SMART_N_SCORES; ++k) a.scores[m * SMART_N_SCORES + k] = sc[k];
-        }
-        if (a.best_sign != 0 && active) {
-            double t = sc[0];
-#pragma unroll
-            for (int k = 1; k < SMART_N_SCORES; ++k) t = (a.best_col == k) ? sc[k] : t;
-            t = a.best_sign > 0 ? t : -t;
-            target = (t == t) ? t : -CUDART_INF;
-        }
-    }
-    if (a.gw != nullptr && active) a.gw[m] = gw;
+    const double target = write_member_results<BLOCK>(a, sm.acc + tid, m, active, c, gw);
     if (kVariant == kVariantFluxes && a.last_state != nullptr && active) {
         // the 7 fluxes of the last step in m3/s, the 12 states back in m3 (structure.py:259-264)
         double *ls = a.last_state + m * SMART_N_VARS;
@@ -551,39 +607,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         for (int k = 0; k < 6; ++k) ls[12 + k] = static_cast<double>(s.ly[k]) * to_m3;
         ls[18] = static_cast<double>(s.riv) * to_m3;
     }
-    if (a.best_sign != 0) {
-        // arg-max over the CTA with warp shuffles; ties go to the lower member index
-        long long idx = active ? m : 0x7fffffffffffffffLL;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const double ot = __shfl_xor_sync(0xffffffffu, target, off);
-            const long long oi = __shfl_xor_sync(0xffffffffu, idx, off);
-            if (ot > target || (ot == target && oi < idx)) {
-                target = ot;
-                idx = oi;
-            }
-        }
-        __syncthreads();   // the accumulator slots are free to reuse now
-        double *s_t = sm.acc;
-        long long *s_idx = reinterpret_cast<long long *>(sm.acc + BLOCK);
-        if ((tid & 31) == 0) {
-            s_t[tid >> 5] = target;
-            s_idx[tid >> 5] = idx;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            for (int w = 1; w < BLOCK / 32; ++w) {
-                const double ot = s_t[w];
-                const long long oi = s_idx[w];
-                if (ot > target || (ot == target && oi < idx)) {
-                    target = ot;
-                    idx = oi;
-                }
-            }
-            a.blk_best_score[blockIdx.x] = target;
-            a.blk_best_index[blockIdx.x] = idx;
-        }
-    }
+    if (a.best_sign != 0) cta_best<BLOCK>(a, sm.acc, target, active ? m : 0x7fffffffffffffffLL);
 }
 
 // Variant of the step a kernel instantiation carries.  The choice depends on the members'
@@ -606,13 +630,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
     for (int k = 0; k < SMART_N_PARAMS; ++k) par[k] = a.params[m * SMART_N_PARAMS + k];
 
     if (kVariant != kVariantFluxes) {
-        // The merged form is exact only when no clamp, cap or leak predicate can fire:
-        // every routing constant >= dt, inflows >= 0 (0 <= D <= 1, 0 <= H < 1), s' < 1.
-        const double dt = a.dt;
-        bool fast_ok = par[6] * 3600.0 >= dt && par[7] * 3600.0 >= dt && par[8] * 3600.0 >= dt &&
-                       par[9] * 3600.0 >= dt && par[4] >= 0.0 && par[4] <= 0.5 && par[5] > 0.0 &&
-                       par[3] >= 0.0 && par[3] <= 1.0 && par[2] >= 0.0 && par[2] <= 0.99 && par[0] > 0.0;
-        fast_ok = fast_ok && !a.force_general && a.initial_state == nullptr;
+        const bool fast_ok = fast_form_ok(par, a.dt) && !a.force_general && a.initial_state == nullptr;
         const int need_general = __syncthreads_or(fast_ok ? 0 : 1);
         if ((need_general != 0) != (kVariant == kVariantGeneral)) return;   // the other launch owns this CTA
     }

@@ -423,6 +423,79 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
 #endif
 constexpr int kWetUnroll = SMART_WET_UNROLL;   // unroll factor of the wet-block hour loop
 
+// Dry block in closed form (see above): soil per member in phases, stores + river + the two
+// running sums by the linear recurrences.  Always binary64 arithmetic, whatever R is.
+template <typename R, int kStride>
+__device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, const double *kb, double ex_d, int rep,
+                                               R &acc, R &agw)
+{
+    // Soil over the whole dry block, per member (a member's arithmetic never depends on the
+    // other lanes of its warp).  Nothing refills the layers, so each one runs empty at most
+    // once: while layers 0..k-1 are empty the demand reaching layer k is C^k d0 per step
+    // (:418).  A layer that is already empty only passes the demand on, decayed by C; otherwise
+    // it serves floor(level / demand) whole steps in one multiplication, then one ordinary
+    // ladder step (from k down) empties it and the demand decays by C again.
+    double left = static_cast<double>(rep);      // steps of the block still to account for
+    double dem = -ex_d;                          // demand arriving at layer k in each of them
+    const double C = static_cast<double>(kc[0]);
+    double ly[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ly[k] = static_cast<double>(s.ly[k]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        if (__any_sync(__activemask(), left > 0.0)) {
+            if (left > 0.0) {
+                bool moves_on = true;            // the demand reaches layer k + 1
+                if (ly[k] > 0.0) {
+                    // Level if the layer served every remaining step.  Not negative <=> the exact
+                    // quotient level / demand is >= left <=> floor(level / dem) >= left (left is a
+                    // whole number, rounding is monotonic): the usual case, decided without dividing.
+                    const double served = fma(-left, dem, ly[k]);
+                    if (sign_clear(served)) {
+                        ly[k] = served;
+                        left = 0.0;
+                        moves_on = false;
+                    } else {
+                        // whole steps this layer can serve before it runs empty
+                        const double can = floor(ly[k] / dem);
+                        const double n_full = can < left ? can : left;
+                        ly[k] = fma(-n_full, dem, ly[k]);
+                        left -= n_full;
+                        if (left > 0.0) {        // transition step: layer k cannot meet the demand
+                            double d = dem;
+#pragma unroll
+                            for (int j = k; j < 6; ++j) {
+                                const double t = ly[j] - d;
+                                const bool enough = sign_clear(t);
+                                ly[j] = enough ? t : 0.0;
+                                d = enough ? 0.0 : C * (-t);
+                            }
+                            left -= 1.0;
+                        } else {
+                            moves_on = false;
+                        }
+                    }
+                }
+                if (moves_on) dem *= C;
+            }
+        }
+    }
+    // (after layer 5 nothing is left to take: remaining steps of the block change nothing)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(ly[k]);
+    const double a = static_cast<double>(s.ove), b = static_cast<double>(s.itf);
+    const double g = static_cast<double>(s.sgw), w = static_cast<double>(s.riv);
+    const double a_n = a * kb[0 * kStride], b_n = b * kb[1 * kStride], g_n = g * kb[2 * kStride];
+    const double w_n = fma(kb[4 * kStride], a, fma(kb[5 * kStride], b, fma(kb[6 * kStride], g, w * kb[3 * kStride])));
+    const double out_g = g - g_n;
+    agw += static_cast<R>(out_g);
+    acc += static_cast<R>(((w - w_n) + (a - a_n)) + ((b - b_n) + out_g));
+    s.ove = static_cast<R>(a_n);
+    s.itf = static_cast<R>(b_n);
+    s.sgw = static_cast<R>(g_n);
+    s.riv = static_cast<R>(w_n);
+}
+
 template <typename R, int kStride>
 __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPar<R> &p, const R *kc, const double *kb,
                                                  FastCarry<R> &carry, double ex_d, int rep, R &acc, R &agw)
@@ -451,56 +524,8 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
         }
         acc += sum_riv * kc[6 * kStride];
     } else {
-        // Soil over the whole dry block, per member (a member's arithmetic never depends on the
-        // other lanes of its warp).  Nothing refills the layers, so each one runs empty at most
-        // once: while layers 0..k-1 are empty the demand reaching layer k is C^k d0 per step
-        // (:418), it serves floor(level / demand) whole steps in one multiplication, then one
-        // ordinary ladder step (from k down) empties it and the demand decays by C again.
-        double left = static_cast<double>(rep);      // steps of the block still to account for
-        double dem = -ex_d;                          // demand arriving at layer k in each of them
-        const double C = static_cast<double>(kc[0]);
-        double ly[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) ly[k] = static_cast<double>(s.ly[k]);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            if (__any_sync(__activemask(), left > 0.0)) {
-                if (left > 0.0) {
-                    // whole steps this layer can serve; dem == 0 (C == 0) asks nothing of it
-                    const double can = dem > 0.0 ? floor(ly[k] / dem) : left;
-                    const double n_full = can < left ? can : left;
-                    ly[k] = fma(-n_full, dem, ly[k]);
-                    left -= n_full;
-                    if (left > 0.0) {                // transition step: layer k cannot meet the demand
-                        double d = dem;
-#pragma unroll
-                        for (int j = k; j < 6; ++j) {
-                            const double t = ly[j] - d;
-                            const bool enough = sign_clear(t);
-                            ly[j] = enough ? t : 0.0;
-                            d = enough ? 0.0 : C * (-t);
-                        }
-                        left -= 1.0;
-                        dem *= C;
-                    }
-                }
-            }
-        }
-        // (after layer 5 nothing is left to take: remaining steps of the block change nothing)
-#pragma unroll
-        for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(ly[k]);
+        dry_block_fast<R, kStride>(s, kc, kb, ex_d, rep, acc, agw);
         carry.valid = false;
-        const double a = static_cast<double>(s.ove), b = static_cast<double>(s.itf);
-        const double g = static_cast<double>(s.sgw), w = static_cast<double>(s.riv);
-        const double a_n = a * kb[0 * kStride], b_n = b * kb[1 * kStride], g_n = g * kb[2 * kStride];
-        const double w_n = fma(kb[4 * kStride], a, fma(kb[5 * kStride], b, fma(kb[6 * kStride], g, w * kb[3 * kStride])));
-        const double out_g = g - g_n;
-        agw += static_cast<R>(out_g);
-        acc += static_cast<R>(((w - w_n) + (a - a_n)) + ((b - b_n) + out_g));
-        s.ove = static_cast<R>(a_n);
-        s.itf = static_cast<R>(b_n);
-        s.sgw = static_cast<R>(g_n);
-        s.riv = static_cast<R>(w_n);
     }
 }
 
