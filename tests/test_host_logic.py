@@ -268,6 +268,31 @@ def test_library_exports_every_declared_symbol():
     assert "n_members" in _native.last_error()
 
 
+def test_selection_and_sampler_entry_points_validate_before_touching_the_device():
+    """smart_condition_rows / smart_best_rows / smart_lhs_rows reject bad arguments with
+    SMART_ERR_BAD_ARG and a message, before any CUDA call (so this runs without a GPU)."""
+    from smartpy_b200 import _native
+    lib = _native.load()
+    cond = (_native.Condition * 1)(_native.Condition(0, 9, 0.0, 0.0))              # unknown kind
+    assert lib.smart_condition_rows(8, 10, 8, cond, 1, 8, 8, 8, None) == _native.ERR_BAD_ARG
+    assert "kind" in _native.last_error()
+    cond = (_native.Condition * 1)(_native.Condition(8, 1, 0.0, 0.0))              # column outside the table
+    assert lib.smart_condition_rows(8, 10, 8, cond, 1, 8, 8, 8, None) == _native.ERR_BAD_ARG
+    assert "column" in _native.last_error()
+    assert lib.smart_condition_rows(8, 10, 8, cond, _native.MAX_CONDITIONS + 1, 8, 8, 8, None) == _native.ERR_BAD_ARG
+    assert lib.smart_best_rows(8, 10, 8, 0, None, 0, 11, 8, 8, 8, None) == _native.ERR_BAD_ARG   # k > n_rows
+    assert "k must be" in _native.last_error()
+    assert lib.smart_best_rows(8, 10, 8, 8, None, 0, 1, 8, 8, 8, None) == _native.ERR_BAD_ARG    # target column
+    bounds = np.array([[0.0, 1.0]] * 3)
+    assert lib.smart_lhs_rows(1, 10, 5, 6, 3, bounds.ctypes.data, 8, None) == _native.ERR_BAD_ARG   # rows past n_total
+    assert lib.smart_lhs_rows(1, 10, 0, 10, 17, bounds.ctypes.data, 8, None) == _native.ERR_BAD_ARG  # too many columns
+    assert "smart_lhs_rows" in _native.last_error()
+    assert lib.smart_condition_workspace_bytes(1000, 10) >= 8 * 1000
+    # the ctypes mirror of smart_condition: 24 bytes, doubles at 8 and 16
+    assert ctypes.sizeof(_native.Condition) == 24
+    assert (_native.Condition.lo.offset, _native.Condition.hi.offset) == (8, 16)
+
+
 def test_descriptor_layout_matches_header(tmp_path):
     """ctypes mirror vs the C struct: size and every field offset, checked with gcc."""
     from smartpy_b200 import _native
