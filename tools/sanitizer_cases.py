@@ -45,6 +45,22 @@ def main():
         eng = BatchEngine(rain[5:5 + 24 * 30], peva[5:5 + 24 * 30], [1e8, 2e8, 3e8], 3600.0, 1, report='raw',
                           members_per_catchment=mpc)
         eng.run(params[:3 * mpc], discharge=True, scores=False)
+    # conditioning of a score table (mask + ordered compaction, radix select + bitonic sort of the
+    # winners: shared-memory histograms, atomics, multi-chunk sort) and the device sampler
+    from smartpy_b200.montecarlo import conditioning
+    names = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
+    rng = np.random.RandomState(1)
+    table = rng.randn(9001, 8)
+    table[:, 1] = np.round(table[:, 1], 1)
+    table[:, 7] = rng.rand(9001) > 0.5
+    t = torch.from_numpy(table).cuda()
+    for k in (1, 100, 2049, 4100):
+        rows = conditioning.best_rows(t, names, 'KGE', k, {'GW': ('equal', (1.0,))})
+        cases.append(("best_rows k=%d" % k, float(rows[-1])))
+    rows = conditioning.behavioural_rows(t, names, {'NSE': ('min', (0.0,)), 'PBias': ('inside', (-1.0, 1.0))})
+    cases.append(("behavioural_rows", float(rows.numel())))
+    sample = conditioning.latin_hypercube_device(5003, [[0.0, 1.0]] * 10, seed=3, row_first=11, n_rows=4000)
+    cases.append(("latin_hypercube_device", float(sample.sum())))
     torch.cuda.synchronize()
     for name, v in cases:
         print(name, v)
