@@ -23,6 +23,18 @@
 #include <type_traits>
 #include <vector>
 
+// Translation units.  A member's binary64 result must not depend on WHICH instantiation of a
+// kernel advanced it (register budget, CTA size -- chosen from the batch size): left to itself
+// ptxas contracts a * b + c differently from one instantiation to the next.  This file is therefore
+// compiled with -fmad=false: the only FMAs are the ones written in the source, and the host
+// emulation of smart_step.cuh reproduces the GPU bit for bit.  The binary32-state kernels owe the
+// reference a tolerance, not bits, and keep the compiler's contraction (9 % faster): they are
+// compiled as a second translation unit, smart_kernels_f32.cu, which defines SMART_TU_F32 and
+// includes this file -- it then emits smart_batch_run_f32 and nothing else.
+#ifdef SMART_TU_F32
+int smart_internal_fail(int code, const char *msg);     // the error channel lives in the binary64 unit
+#endif
+
 namespace {
 
 using namespace smart;
@@ -49,6 +61,7 @@ constexpr int kStepUnroll = SMART_STEP_UNROLL;   // unroll factor of the per-ste
 #define SMART_FAST_REGS_F32 72     // fast FP32 kernel: 70 registers used, no spills, 28 warps per SM (sweep 64..96)
 #endif
 
+#ifndef SMART_TU_F32
 thread_local std::string g_err;
 
 int fail(int code, const std::string &msg)
@@ -56,6 +69,9 @@ int fail(int code, const std::string &msg)
     g_err = msg;
     return code;
 }
+#else
+int fail(int code, const std::string &msg) { return smart_internal_fail(code, msg.c_str()); }
+#endif
 
 #define SMART_CUDA(expr)                                                                      \
     do {                                                                                      \
@@ -1018,7 +1034,13 @@ struct DevBuf {
 
 }  // namespace
 
-// error channel shared with smart_select.cu
+#ifdef SMART_TU_F32
+extern "C" int smart_batch_run_f32(const smart_batch_desc *d, void *stream)
+{
+    return launch<float>(d, static_cast<cudaStream_t>(stream));
+}
+#else
+// error channel shared with smart_kernels_f32.cu, smart_select.cu and smart_sample.cu
 int smart_internal_fail(int code, const char *msg) { return fail(code, msg); }
 
 // =================================================================== C ABI
@@ -1048,11 +1070,6 @@ int smart_obs_stats(const double *obs, int64_t n_report, int32_t n_catchments, d
 int smart_batch_run_f64(const smart_batch_desc *d, void *stream)
 {
     return launch<double>(d, static_cast<cudaStream_t>(stream));
-}
-
-int smart_batch_run_f32(const smart_batch_desc *d, void *stream)
-{
-    return launch<float>(d, static_cast<cudaStream_t>(stream));
 }
 
 static int stamp_rows(const double *in, int64_t n_in, int32_t n_catchments, int32_t repeat, double div, double *out,
@@ -1179,7 +1196,7 @@ int smart_batch_run_host(const smart_batch_desc *h, int precision, int device)
         d.best_score = static_cast<double *>(bs.p);
         d.best_index = static_cast<int64_t *>(bi.p);
     }
-    rc = precision == 64 ? launch<double>(&d, st) : launch<float>(&d, st);
+    rc = precision == 64 ? launch<double>(&d, st) : smart_batch_run_f32(&d, st);
     if (rc) return rc;
     if (h->discharge) {
         // host layout keeps the caller's leading dimension
@@ -1243,3 +1260,4 @@ int smart_fma_peak_probe(int precision, int blocks, int threads, int64_t iters, 
 }
 
 }  // extern "C"
+#endif  // SMART_TU_F32

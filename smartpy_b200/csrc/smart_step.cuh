@@ -50,7 +50,7 @@ struct StepOut {
 // exact FP64 immediates live in constant memory so that they are operands of the multiply itself
 // instead of being rebuilt with UMOV pairs every wet step.
 #ifndef SMART_HOST_EMULATION
-__device__ __constant__ double smart_inv3 = 1.0 / 3.0, smart_inv5 = 0.2, smart_inv6 = 1.0 / 6.0;
+static __device__ __constant__ double smart_inv3 = 1.0 / 3.0, smart_inv5 = 0.2, smart_inv6 = 1.0 / 6.0;
 #else
 static const double smart_inv3 = 1.0 / 3.0, smart_inv5 = 0.2, smart_inv6 = 1.0 / 6.0;
 #endif
@@ -270,7 +270,7 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
     R tot = carry.tot;
     if (!carry.valid) tot = soil_total(s);
     in_quick = hex * tot;                           // :363-364, h' * excess = (H/Z * excess) * total
-    const R u0 = in_quick - ex;                     // u = -(excess rain still to place) <= 0
+    const R u0 = fma(hex, tot, -ex);                // u = -(excess rain still to place) <= 0
     R u = u0;
     auto fill = [&](int i) {                        // :367-374
         const R w = s.ly[i] - u;                    // level if the layer took everything
@@ -305,7 +305,7 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
 #pragma unroll
         for (int i = 0; i < 6; ++i) s.ly[i] = fma(-s.ly[i], pw[i], s.ly[i]);            // :381-385
         const R tot1 = soil_total(s);
-        in_int += tot_f - tot1;
+        in_int = fma(omD, -u, tot_f - tot1);                                            // :377 + interflow
 #pragma unroll
         for (int i = 0; i < 6; ++i) {                                                   // :388-399
             const R f2 = i == 0 ? sp : sp * inv_const<R>(i);
@@ -522,7 +522,7 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
             s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - s.itf * r_fk) + in_int;
             s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
         }
-        acc += sum_riv * kc[6 * kStride];
+        acc = kOneFma ? fma(sum_riv, kc[6 * kStride], acc) : acc + sum_riv * kc[6 * kStride];
     } else {
         dry_block_fast<R, kStride>(s, kc, kb, ex_d, rep, acc, agw);
         carry.valid = false;
