@@ -268,6 +268,17 @@ def test_library_exports_every_declared_symbol():
     assert "n_members" in _native.last_error()
 
 
+def test_binary64_unit_is_built_without_implicit_contraction():
+    """The determinism of binary64 results across kernel instantiations rests on -fmad=false for
+    smart_kernels.cu (tests/test_gpu_fullsize.py); the FP32-state unit keeps the default."""
+    from smartpy_b200 import _build
+    units = dict(_build.UNITS)
+    assert units["smart_kernels.cu"] == ["-fmad=false"]
+    assert units["smart_kernels_f32.cu"] == []
+    src = open(os.path.join(ROOT, "smartpy_b200", "csrc", "smart_kernels_f32.cu")).read()
+    assert "#define SMART_TU_F32" in src and '#include "smart_kernels.cu"' in src
+
+
 def test_selection_and_sampler_entry_points_validate_before_touching_the_device():
     """smart_condition_rows / smart_best_rows / smart_lhs_rows reject bad arguments with
     SMART_ERR_BAD_ARG and a message, before any CUDA call (so this runs without a GPU)."""
