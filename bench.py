@@ -49,10 +49,6 @@ METRIC = "member-timesteps/s"
 # faithful restatement (FMA = one instruction): 65.5 on a dry step, 135.5 on a wet step.
 I_DRY, I_WET = 65.5, 135.5
 
-# smart_batch_run_* launches the fast kernel and the general kernel back to back (each CTA runs
-# in exactly one of them, smart_kernels.cu)
-KERNELS_PER_RUN = 2
-
 # members each host worker simulates per CPU-arm step (C oracle: ~26 ms per 96k-step member)
 CPU_MEMBERS_PER_WORKER = 96      # a bounded sample: a few seconds of wall time per CPU-arm step on 16 cores
 
@@ -325,11 +321,9 @@ def main():
     block = torch.empty((n, 9), dtype=torch.float64, device=dev) if world > 1 else None
     # L2 flush between timed iterations: overwrite a buffer twice the size of the 126 MB L2
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    launches = [0]
 
     def step_resident():
         res = eng.run(p_dev, discharge=w["discharge"], scores=scored, gw=True, out=out)
-        launches[0] += KERNELS_PER_RUN
         if world > 1:
             block[:, :8] = res["scores"] if scored else 0.0
             block[:, 8] = res["gw"]
@@ -345,7 +339,6 @@ def main():
     def step_e2e():
         p_stage.copy_(p_pin, non_blocking=True)
         res = eng.run(p_stage, discharge=w["discharge"], scores=scored, gw=True, out=out)
-        launches[0] += KERNELS_PER_RUN
         if scored:
             sc_pin.copy_(res["scores"], non_blocking=True)
         gw_pin.copy_(res["gw"], non_blocking=True)
@@ -381,7 +374,7 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    launches[0] = 0
+    launches_before = eng.kernel_launches
     barrier()
     ms_value = timed(step_resident, args.steps)
     barrier()
@@ -392,7 +385,7 @@ def main():
         ms_e2e = timed(step_e2e, args.steps)
         barrier()
     clocks = sampler.stop() if rank == 0 else None
-    n_launches = launches[0]
+    n_launches = eng.kernel_launches - launches_before     # counted by the engine, kernel by kernel
 
     # max over ranks (device time)
     if world > 1:

@@ -108,6 +108,14 @@ typedef struct smart_batch_desc {
     double *best_score;             /* [1] */
     int64_t *best_index;            /* [1] */
     void *workspace;                /* smart_batch_workspace_bytes() bytes when best_sign != 0 */
+
+    /* ---- grouping of members into warps (optional, device): a permutation of 0..n_members-1;
+     *      thread i of the launch advances member member_order[i] and writes that member's
+     *      outputs at the member's own index.  Outputs are unchanged bit for bit (a member's
+     *      result does not depend on its neighbours); only the divergence inside a warp changes --
+     *      sorted by T, the members of a warp agree on which steps are wet.  Needs
+     *      n_catchments == 1 and no discharge / last_state / initial_state. */
+    const int64_t *member_order;
 } smart_batch_desc;
 
 int smart_version(void);

@@ -84,6 +84,7 @@ class BatchDesc(ctypes.Structure):
         ("best_score", ctypes.c_void_p),
         ("best_index", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p),
+        ("member_order", ctypes.c_void_p),
     ]
 
 

@@ -86,6 +86,7 @@ struct KArgs {
     double *scores, *gw, *last_state;
     double *blk_best_score;
     long long *blk_best_index;
+    const long long *order;      // optional permutation: thread i advances member order[i]
     long long N, T, W, ld_q;
     int C, mpc, gap, report_type;
     int chunk, kc, use_tma, force_general;
@@ -639,7 +640,8 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
     const int tid = threadIdx.x;
     const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + tid;
     const bool active = m_raw < a.N;
-    const long long m = active ? m_raw : a.N - 1;   // tail threads shadow the last member, store nothing
+    long long m = active ? m_raw : a.N - 1;         // tail threads shadow the last member, store nothing
+    if (a.order != nullptr) m = a.order[m];         // (single catchment, no [t][member] output: validate())
 
     double par[SMART_N_PARAMS];
 #pragma unroll
@@ -877,6 +879,9 @@ int validate(const smart_batch_desc *d, bool host_mode = false)
     }
     if (d->discharge && d->ld_discharge < d->n_members)
         return fail(SMART_ERR_BAD_ARG, "ld_discharge must be >= n_members");
+    if (d->member_order && (d->n_catchments != 1 || d->discharge || d->last_state || d->initial_state || host_mode))
+        return fail(SMART_ERR_BAD_ARG,
+                    "member_order needs one catchment, device pointers and no discharge/last_state/initial_state");
     if (d->best_sign != 0) {
         if (!d->obs || (!d->workspace && !host_mode))
             return fail(SMART_ERR_BAD_ARG, "best member needs obs and workspace");
@@ -920,6 +925,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     a.force_general = (d->flags & SMART_FLAG_FORCE_GENERAL) ? 1 : 0;
     a.best_col = d->best_column;
     a.best_sign = d->best_sign;
+    a.order = reinterpret_cast<const long long *>(d->member_order);
     // first reporting step of the main run, 1-based: [::-gap][::-1] counts back from the end
     const int64_t n_rep = n_report_of(d);
     a.first_report = static_cast<int>(d->n_steps - (n_rep - 1) * d->report_gap);

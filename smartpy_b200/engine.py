@@ -20,6 +20,8 @@ SCORE_NAMES = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
 
 # engine-level flag (not passed to the library): always hand the kernel one forcing row per step
 FLAG_NO_BLOCK_MODE = 0x10000
+FLAG_NO_REORDER = 0x20000     # engine-level: keep the members in sample order inside the launch
+REORDER_MIN_MEMBERS = 4096    # below this the sort costs more than the divergence it removes
 
 
 def _torch():
@@ -68,6 +70,9 @@ class BatchEngine(object):
         self.warm_up_steps = int(warm_up_steps)
         self.extra = extra
         self.gw_constraint = gw_constraint
+        self._order_work = None
+        #: kernels launched by run() so far (bench.py reports the count of its timed region)
+        self.kernel_launches = 0
 
         rain = torch.as_tensor(np.ascontiguousarray(rain, dtype=np.float64) if not torch.is_tensor(rain) else rain)
         peva = torch.as_tensor(np.ascontiguousarray(peva, dtype=np.float64) if not torch.is_tensor(peva) else peva)
@@ -272,11 +277,58 @@ class BatchEngine(object):
         fn = self.lib.smart_batch_run_f64 if self.precision == 'f64' else self.lib.smart_batch_run_f32
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
+            if (self.n_catchments == 1 and n >= REORDER_MIN_MEMBERS and not discharge and not last_state
+                    and initial_state is None and not (self.flags & FLAG_NO_REORDER)):
+                order = self._order_by_wetness(p_dev, n, stream)
+                d.member_order = order.data_ptr()
+                keep.append(order)
+                self.kernel_launches += self._best_rows_launches(n, n)
             rc = fn(ctypes.byref(d), stream.cuda_stream)
         _native.check(rc)
+        # the step kernel is launched in its merged and in its branch-faithful form (each CTA runs in
+        # exactly one of them); last_state takes the single flux-reporting kernel; + the best-member finalize
+        self.kernel_launches += (1 if last_state else (1 if (self.flags & _native.FLAG_FORCE_GENERAL) or
+                                                       initial_state is not None else 2)) + (1 if best else 0)
         for t in keep:   # keep inputs alive until the stream has consumed them
             t.record_stream(stream)
         return res
+
+    @staticmethod
+    def _best_rows_launches(n, k):
+        """Kernel launches of one smart_best_rows(n, k) call (mirrors the loop in smart_select.cu)."""
+        padded = 1
+        while padded < k:
+            padded <<= 1
+        chunk = min(padded, 2048)
+        launches = 2 + 24 + 1 + (1 if padded > k else 0) + 1      # init, keys, 12 x (histogram, pick), gather, pad, emit
+        if padded > 1:
+            launches += 1
+            kk = 2 * chunk
+            while kk <= padded:
+                j = kk >> 1
+                while j >= chunk:
+                    launches += 1
+                    j >>= 1
+                launches += 1
+                kk <<= 1
+        return launches
+
+    def _order_by_wetness(self, p_dev, n, stream):
+        """Member indices sorted by T (params column 0), on the device with the library's own
+        radix select + sort (smart_best_rows with k = n).  Whether a step is wet depends on the
+        member through `rain * T - peva >= 0` only, so warps of neighbouring T agree on it and do
+        not walk a wet block for the sake of a few of their lanes (3-4 % of the wet-block work of
+        an LHS sample in sample order).  Results do not change by a bit: a member's arithmetic
+        never depends on its neighbours."""
+        torch = _torch()
+        order = torch.empty((n,), dtype=torch.int64, device=self.device)
+        nbytes = self.lib.smart_condition_workspace_bytes(n, n)
+        work = self._order_work
+        if work is None or work.numel() < nbytes:
+            work = self._order_work = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        _native.check(self.lib.smart_best_rows(p_dev.data_ptr(), n, _native.N_PARAMS, 0, None, 0, n,
+                                               order.data_ptr(), None, work.data_ptr(), stream.cuda_stream))
+        return order
 
     # steps one launch of n members walks through (warm-up + main), for throughput accounting
     def member_steps(self, n_members):

@@ -109,3 +109,41 @@ def test_c3_full_batch_planted_members_match_oracle(oracle_lib):
     assert np.max(np.abs(sc[spots][:, :7] - sc_ref[:, :7]) / np.maximum(1.0, np.abs(sc_ref[:, :7]))) < 1e-10
     assert np.array_equal(sc[spots][:, 7], sc_ref[:, 7])
     assert relmax(gw[spots], gw_ref) < 1e-9
+
+
+@pytest.mark.parametrize("flags", [0, 0x10000])        # block mode, per-step path
+def test_member_order_changes_no_bit(catchment, flags):
+    """BatchEngine sorts the members of a launch by T on the device (member_order of the C ABI) so
+    that the lanes of a warp agree on wet and dry steps; FLAG_NO_REORDER keeps the sample order.
+    Same scores, gw and best member, bit for bit; and the C ABI refuses an order it cannot honour."""
+    import ctypes
+    import torch
+    import bench
+    from smartpy_b200 import _native
+    from smartpy_b200.engine import FLAG_NO_REORDER, REORDER_MIN_MEMBERS
+    g = load_golden("runs_members")
+    n = 3 * REORDER_MIN_MEMBERS + 17
+    params, spots = _planted_batch(n, g["params"], 9)
+    params[5, 0] = params[6, 0] = params[n - 1, 0]              # ties on the sort key
+    n_steps = 24 * 500
+    a = make_engine(catchment, n_steps=n_steps, flags=flags)
+    b = make_engine(catchment, n_steps=n_steps, flags=flags | FLAG_NO_REORDER)
+    ra = a.run(params, discharge=False, scores=True, gw=True, best=("KGE", 1))
+    rb = b.run(params, discharge=False, scores=True, gw=True, best=("KGE", 1))
+    assert a.kernel_launches > b.kernel_launches == 3          # the sort ran only in `a`
+    assert np.array_equal(ra["scores"].cpu().numpy(), rb["scores"].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(ra["gw"].cpu().numpy(), rb["gw"].cpu().numpy())
+    assert int(ra["best"][1].item()) == int(rb["best"][1].item())
+    assert float(ra["best"][0].item()) == float(rb["best"][0].item())
+    # discharge wanted: the order is not used (the [t][member] stores must stay coalesced)
+    before = a.kernel_launches
+    a.run(params[:REORDER_MIN_MEMBERS], discharge=True, scores=False)
+    assert a.kernel_launches - before == 2
+    # the ABI itself: member_order with a discharge buffer is refused before any launch
+    d = a._desc(8)
+    d.params = d.rain = d.peva = d.area_m2 = 8
+    d.member_order = 8
+    d.discharge, d.ld_discharge = 8, 8
+    assert a.lib.smart_batch_run_f64(ctypes.byref(d), None) == _native.ERR_BAD_ARG
+    assert "member_order" in _native.last_error()
+
