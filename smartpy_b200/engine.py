@@ -22,6 +22,7 @@ SCORE_NAMES = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
 FLAG_NO_BLOCK_MODE = 0x10000
 FLAG_NO_REORDER = 0x20000     # engine-level: keep the members in sample order inside the launch
 REORDER_MIN_MEMBERS = 4096    # below this the sort costs more than the divergence it removes
+ORDER_T_BUCKETS = 64.0        # slices of the T range inside which members are ordered by S
 
 
 def _torch():
@@ -314,19 +315,29 @@ class BatchEngine(object):
         return launches
 
     def _order_by_wetness(self, p_dev, n, stream):
-        """Member indices sorted by T (params column 0), on the device with the library's own
-        radix select + sort (smart_best_rows with k = n).  Whether a step is wet depends on the
-        member through `rain * T - peva >= 0` only, so warps of neighbouring T agree on it and do
-        not walk a wet block for the sake of a few of their lanes (3-4 % of the wet-block work of
-        an LHS sample in sample order).  Results do not change by a bit: a member's arithmetic
-        never depends on its neighbours."""
+        """Member indices grouped so that the lanes of a warp take the same branches, sorted on the
+        device with the library's own radix select + sort (smart_best_rows with k = n).
+
+        Key = bucket of T (ORDER_T_BUCKETS equal slices of the sample's range) + S scaled into
+        [0, 1).  Whether a step is wet depends on the member through `rain * T - peva >= 0` only:
+        with neighbouring T a warp no longer walks a wet block for the sake of a few lanes
+        (3-4 % of the wet-block work of an LHS sample in sample order).  Inside a slice of T the
+        members are ordered by S, which sets how much room the leaks open in the top soil layer
+        every hour, i.e. whether the fill ladder stops after the first layer for the whole warp.
+        Results do not change by a bit: a member's arithmetic never depends on its neighbours."""
         torch = _torch()
         order = torch.empty((n,), dtype=torch.int64, device=self.device)
         nbytes = self.lib.smart_condition_workspace_bytes(n, n)
         work = self._order_work
         if work is None or work.numel() < nbytes:
             work = self._order_work = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
-        _native.check(self.lib.smart_best_rows(p_dev.data_ptr(), n, _native.N_PARAMS, 0, None, 0, n,
+        t, x = p_dev[:, 0], p_dev[:, 4]
+        tmin, tmax = torch.aminmax(t)
+        xmin, xmax = torch.aminmax(x)
+        slices = torch.clamp(torch.floor((t - tmin) / (tmax - tmin + 1e-300) * ORDER_T_BUCKETS), max=ORDER_T_BUCKETS - 1)
+        key = (slices + (x - xmin) / (xmax - xmin + 1e-300) * 0.999).contiguous()
+        key.record_stream(stream)
+        _native.check(self.lib.smart_best_rows(key.data_ptr(), n, 1, 0, None, 0, n,
                                                order.data_ptr(), None, work.data_ptr(), stream.cuda_stream))
         return order
 
