@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Measured parity of the CUDA path against the reference-generated goldens (run on the GPU box):
 
-    python tools/parity_report.py > profiles/rNN_parity_report.txt
+    python tests/parity_report.py > profiles/rNN_parity_report.txt
 """
 import os
 import sys

@@ -25,6 +25,6 @@ ncu --set full --clock-control none --import-source on -k regex:smart_batch_kern
 python tools/bench_conditioning.py 10000000 > $O/conditioning_bench_$R.json
 python bench.py --flags 65536 --steps 3 --no-cpu-baseline > $O/bench_${R}_c2_perstep.json
 python bench.py --flags 1 --steps 3 --no-cpu-baseline > $O/bench_${R}_c2_general.json
-python tools/parity_report.py > $O/parity_report_$R.txt
+python tests/parity_report.py > $O/parity_report_$R.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/smi_$R.csv
 ls -la $O
