@@ -268,6 +268,26 @@ def test_library_exports_every_declared_symbol():
     assert "n_members" in _native.last_error()
 
 
+def test_member_order_key_groups_by_t_slice_then_s_times_z():
+    """engine.member_order_key on a CPU tensor (the sort itself is the library's, GPU-tested):
+    sorting by the key = numpy lexsort on (slice of T, S * Z); degenerate samples do not divide by 0."""
+    import torch
+    from smartpy_b200.engine import member_order_key, ORDER_T_BUCKETS
+    from smartpy_b200.montecarlo.lhs import latin_hypercube
+    from smartpy_b200.parameters import Parameters
+    p = Parameters()
+    params = latin_hypercube(5000, [p.ranges[n] for n in p.names], rng=np.random.RandomState(2))
+    key = member_order_key(torch.from_numpy(params))
+    assert key.shape == (5000,) and key.dtype == torch.float64 and key.is_contiguous()
+    key = key.numpy()
+    T, SZ = params[:, 0], params[:, 4] * params[:, 5]
+    slices = np.minimum(np.floor((T - T.min()) / (T.max() - T.min() + 1e-300) * ORDER_T_BUCKETS), ORDER_T_BUCKETS - 1)
+    assert np.array_equal(np.floor(key), slices) and slices.max() == ORDER_T_BUCKETS - 1
+    assert np.array_equal(np.argsort(key, kind='stable'), np.lexsort((SZ, slices)))
+    same = np.tile(params[:1], (10, 1))
+    assert np.array_equal(member_order_key(torch.from_numpy(same)).numpy(), np.zeros(10))
+
+
 def test_binary64_unit_is_built_without_implicit_contraction():
     """The determinism of binary64 results across kernel instantiations rests on -fmad=false for
     smart_kernels.cu (tests/test_gpu_fullsize.py); the FP32-state unit keeps the default."""
