@@ -9,8 +9,6 @@ ordered compaction) and ``smart_best_rows`` (radix select of the k best + sort o
 best last), numpy's NaN-sorts-last rule and the literal 'outside' rule.  CUDA tensors only:
 the file-based GLUE/Best classes keep the numpy rules (``montecarlo.condition_mask``).
 """
-import ctypes
-
 import numpy as np
 
 from .. import _native

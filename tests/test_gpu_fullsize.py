@@ -15,8 +15,8 @@ so parity is carried by size-independent properties:
 import numpy as np
 import pytest
 
-from conftest import load_golden, EXTRA
-from test_gpu_parity import make_engine, relmax, RTOL_Q, ATOL_F32
+from conftest import load_golden
+from test_gpu_parity import make_engine, relmax, ATOL_F32
 
 pytestmark = pytest.mark.gpu
 
