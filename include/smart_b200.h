@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SMART_B200_VERSION 100 /* 0.1.0 */
+#define SMART_B200_VERSION 200 /* 0.2.0 */
 
 #define SMART_N_PARAMS 10
 #define SMART_N_VARS 19
@@ -72,8 +72,11 @@ typedef struct smart_batch_desc {
     int32_t forcing_repeat;         /* 0 or 1: rain/peva hold one row per step.  k > 1: one row per block
                                        of k steps with constant forcing (what the reference's daily ->
                                        hourly split produces, timeframe.py:167-186), values already per
-                                       STEP (daily total / k); rows = n_steps / k.  Needs report_gap == k,
-                                       SMART_REPORT_SUMMARY, n_steps % k == n_warmup % k == 0. */
+                                       STEP (daily total / k); rows = n_steps / k.  Needs n_steps % k ==
+                                       n_warmup % k == 0 and a report_gap that divides k ('summary' or
+                                       'raw'; gap == k with 'summary' advances dry blocks in closed form,
+                                       any other gap walks the stores hour by hour and reports inside the
+                                       block, as structure.py:181-195 does for every gap with one loop). */
     double dt_sec;                  /* simulation time step in seconds */
 
     /* ---- inputs */
@@ -97,8 +100,8 @@ typedef struct smart_batch_desc {
     /* ---- outputs (any may be NULL) */
     void *discharge;                /* [n_report][ld_discharge] m3/s; double (f64 entry) or float (f32 entry) */
     int64_t ld_discharge;           /* >= N */
-    double *scores;                 /* [N][8]; GW column is NaN when the constraint is off */
-    double *gw;                     /* [N] groundwater share of runoff (structure.py:191, :194-195) */
+    double *scores;                 /* [N][ld_scores]; GW column is NaN when the constraint is off */
+    double *gw;                     /* [N * ld_gw] groundwater share of runoff (structure.py:191, :194-195) */
     double *last_state;             /* [N][19] state after the last step (structure.py:197) */
 
     /* ---- best member (optional): arg-max (best_sign > 0) or arg-min (< 0) of scores column
@@ -116,10 +119,23 @@ typedef struct smart_batch_desc {
      *      sorted by T, the members of a warp agree on which steps are wet.  Needs
      *      n_catchments == 1 and no discharge / last_state / initial_state. */
     const int64_t *member_order;
+
+    /* ---- leading dimensions of the score outputs (0 = the packed defaults 8 and 1).  With
+     *      ld_scores = ld_gw = 9, scores = block and gw = block + 8 the kernel writes the
+     *      [N][9] block that a sharded run all-gathers, with no packing pass in between. */
+    int64_t ld_scores;
+    int64_t ld_gw;
+    /* ---- slots in member_order (0 = n_members).  smart_member_order() emits
+     *      smart_member_order_len(N) slots: the members that qualify for the fast form first, padded
+     *      with idle slots (-1) to a CTA boundary, then the members that need the branch-faithful
+     *      form -- so that no CTA mixes the two. */
+    int64_t member_order_len;
 } smart_batch_desc;
 
 int smart_version(void);
 const char *smart_last_error(void);
+/* Kernels this library has launched since it was loaded (all entry points, all threads). */
+int64_t smart_launch_count(void);
 
 /* n_report implied by a descriptor: T/gap (summary) or ceil(T/gap) (raw). */
 int64_t smart_batch_n_report(const smart_batch_desc *d);
@@ -157,9 +173,35 @@ int smart_score_discharge(const void *discharge, int64_t ld_discharge, int64_t n
 
 /*
  * Same, with HOST pointers everywhere in *d (workspace/obs_stats ignored: handled inside).
- * Allocates device buffers, copies in, runs, copies out, synchronises.  precision: 64 | 32.
+ * Copies in, runs, copies out, synchronises.  precision: 64 | 32.  Device buffers come from a
+ * grow-only arena kept per host thread and device (no cudaMalloc on the steady path);
+ * smart_host_arena_release() frees it.
  */
 int smart_batch_run_host(const smart_batch_desc *d, int precision, int device);
+int smart_host_arena_release(void);
+
+/*
+ * Grouping of the members of a launch (device pointers, stream-ordered, no allocation): writes
+ * smart_member_order_len(n_members) slots into order_out -- see smart_batch_desc.member_order_len.
+ * Inside each group the members are sorted so that the lanes of a warp take the same branches:
+ * first by slice of T (the wet/dry predicate rain * T - peva >= 0 depends on the member through T
+ * only), then by S * Z (how much room the leaks open in the top soil layer each hour).  Results
+ * of a run do not change by a bit.  workspace: smart_member_order_workspace_bytes(n_members).
+ */
+int64_t smart_member_order_len(int64_t n_members);
+size_t smart_member_order_workspace_bytes(int64_t n_members);
+int smart_member_order(const double *params, int64_t n_members, double dt_sec, int64_t *order_out, void *workspace,
+                       void *stream);
+
+/*
+ * Is rows[n_rows][C] constant inside aligned blocks of k rows?  If so writes the folded series
+ * out[n_rows / k][C] (one row per block) and sets *flag_out (device int32) to 1, else to 0.
+ * n_rows must be a multiple of k.  This is how a per-step series produced by the reference's
+ * daily -> hourly split (timeframe.py:167-186) is recognised and handed to the kernel as one row
+ * per block (forcing_repeat = k).
+ */
+int smart_fold_blocks(const double *rows, int64_t n_rows, int32_t n_catchments, int32_t k, double *out,
+                      int32_t *flag_out, void *stream);
 
 /*
  * Drop-in for smartcpp.allsteps (structure.py:118-121, :143-146), host pointers:

@@ -30,10 +30,11 @@ FLAG_NO_TMA = 0x2
 
 # every symbol include/smart_b200.h declares
 SYMBOLS = (
-    "smart_version", "smart_last_error", "smart_batch_n_report", "smart_batch_workspace_bytes",
+    "smart_version", "smart_last_error", "smart_launch_count", "smart_batch_n_report", "smart_batch_workspace_bytes",
     "smart_obs_stats", "smart_batch_run_f64", "smart_batch_run_f32", "smart_score_discharge",
     "smart_disaggregate", "smart_expand", "smart_stamp", "smart_batch_run_host",
-    "smart_allsteps_host", "smart_fma_peak_probe",
+    "smart_allsteps_host", "smart_host_arena_release", "smart_fma_peak_probe",
+    "smart_member_order_len", "smart_member_order_workspace_bytes", "smart_member_order", "smart_fold_blocks",
     "smart_condition_workspace_bytes", "smart_condition_rows", "smart_best_rows",
     "smart_lhs_rows",
 )
@@ -85,6 +86,9 @@ class BatchDesc(ctypes.Structure):
         ("best_index", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p),
         ("member_order", ctypes.c_void_p),
+        ("ld_scores", ctypes.c_int64),
+        ("ld_gw", ctypes.c_int64),
+        ("member_order_len", ctypes.c_int64),
     ]
 
 
@@ -110,6 +114,20 @@ def load():
     lib.smart_version.argtypes = []
     lib.smart_last_error.restype = ctypes.c_char_p
     lib.smart_last_error.argtypes = []
+    lib.smart_launch_count.restype = ctypes.c_int64
+    lib.smart_launch_count.argtypes = []
+    lib.smart_host_arena_release.restype = ctypes.c_int
+    lib.smart_host_arena_release.argtypes = []
+    lib.smart_member_order_len.restype = ctypes.c_int64
+    lib.smart_member_order_len.argtypes = [ctypes.c_int64]
+    lib.smart_member_order_workspace_bytes.restype = ctypes.c_size_t
+    lib.smart_member_order_workspace_bytes.argtypes = [ctypes.c_int64]
+    lib.smart_member_order.restype = ctypes.c_int
+    lib.smart_member_order.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p,
+                                       ctypes.c_void_p, ctypes.c_void_p]
+    lib.smart_fold_blocks.restype = ctypes.c_int
+    lib.smart_fold_blocks.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_void_p]
     lib.smart_batch_n_report.restype = ctypes.c_int64
     lib.smart_batch_n_report.argtypes = [pdesc]
     lib.smart_batch_workspace_bytes.restype = ctypes.c_size_t

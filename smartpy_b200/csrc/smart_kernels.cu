@@ -19,6 +19,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -34,6 +36,8 @@
 #ifdef SMART_TU_F32
 int smart_internal_fail(int code, const char *msg);     // the error channel lives in the binary64 unit
 #endif
+void smart_internal_count(int n);                       // launch counter, shared by every unit
+void *smart_internal_side_stream();                     // per-device side stream (binary64 unit)
 
 namespace {
 
@@ -57,6 +61,10 @@ constexpr int kStepUnroll = SMART_STEP_UNROLL;   // unroll factor of the per-ste
 #ifndef SMART_SLOW_REGS
 #define SMART_SLOW_REGS 128         // branch-faithful kernels (general, fluxes)
 #endif
+#ifndef SMART_LEAN_RATE
+#define SMART_LEAN_RATE 0.94        // throughput of the lean fast kernel relative to the roomy one at steady state
+#endif
+constexpr double kLeanRate = SMART_LEAN_RATE;
 #ifndef SMART_FAST_REGS_F32
 #define SMART_FAST_REGS_F32 72     // fast FP32 kernel: 70 registers used, no spills, 28 warps per SM (sweep 64..96)
 #endif
@@ -80,18 +88,66 @@ int fail(int code, const std::string &msg) { return smart_internal_fail(code, ms
             return fail(SMART_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));  \
     } while (0)
 
+// kernels launched by this library since it was loaded (smart_launch_count(): bench.py reports
+// the launches of its timed region from this counter, not from a model of the code)
+#ifndef SMART_TU_F32
+std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+#else
+void count_launches(int n) { smart_internal_count(n); }
+#endif
+
+// The stream the branch-faithful kernel runs on beside the fast one (one per device, created on
+// first use, highest priority so that its few CTAs are placed as soon as a slot frees up).  The
+// fork/join events are shared by every caller: the mutex keeps one call's record/wait pairs together.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    std::mutex mu;
+};
+#ifndef SMART_TU_F32
+SideStream *side_stream_impl()
+{
+    static std::mutex create_mu;
+    static SideStream *per_device[64] = {nullptr};
+    static const bool off = getenv("SMART_B200_NO_SIDE_STREAM") != nullptr;
+    if (off) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> hold(create_mu);
+    if (per_device[dev] == nullptr) {
+        SideStream *s = new SideStream;
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, hi) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            delete s;
+            return nullptr;
+        }
+        per_device[dev] = s;
+    }
+    return per_device[dev];
+}
+SideStream *side_stream() { return side_stream_impl(); }
+#else
+SideStream *side_stream() { return static_cast<SideStream *>(smart_internal_side_stream()); }
+#endif
+
 struct KArgs {
     const double *params, *rain, *peva, *area, *obs, *obs_stats, *initial_state;
     void *discharge;
     double *scores, *gw, *last_state;
     double *blk_best_score;
     long long *blk_best_index;
-    const long long *order;      // optional permutation: thread i advances member order[i]
-    long long N, T, W, ld_q;
+    const long long *order;      // optional grouping: thread i advances member order[i] (< 0: idle thread)
+    long long n_threads;         // threads of the launch that may carry a member (N, or the length of order)
+    long long N, T, W, ld_q, ld_s, ld_g;
     int C, mpc, gap, report_type;
     int chunk, kc, use_tma, force_general;
     int has_extra, best_col, best_sign, first_report;
-    int rep, pad0;               // steps per forcing row (1 = one row per step)
+    int rep, mode;               // steps per forcing row (1 = one row per step); kModeStep / kModeBlock / kModeBlockSub
     double dt, aar_ro, split[5], gw_constraint;
 };
 
@@ -168,6 +224,14 @@ __host__ __device__ __forceinline__ int stage_doubles(int chunk, int kc) { retur
 //   double td[BLOCK]               parameter T in binary64 (wet/dry predicate)
 //   double kblock[kBlockSlots][BLOCK]  dry-block constants (block mode only, see smart_block_fast)
 enum : int { kVariantFast = 0, kVariantGeneral = 1, kVariantFluxes = 2 };
+// How the time loop reads the forcing (host: mode_of):
+//   kModeStep     one forcing row per step;
+//   kModeBlock    one row per block of a.rep steps AND one report per block ('summary', gap == rep):
+//                 wet blocks hour by hour, dry blocks in closed form (smart_block_fast);
+//   kModeBlockSub one row per block, reports inside the block (gap divides rep, 'summary' or 'raw'):
+//                 no per-step forcing loads or predicates, dry blocks with the soil in closed form
+//                 and the stores walked hour by hour (every hour's outflow is reported or summed).
+enum : int { kModeStep = 0, kModeBlock = 1, kModeBlockSub = 2 };
 
 template <typename R, int BLOCK>
 struct Smem {
@@ -188,17 +252,18 @@ struct Smem {
 };
 
 // ------------------------------------------------------------------ the time loop
-// kDaily: the forcing arrays hold one row per block of a.rep steps (constant forcing inside the
-// block, the reference's daily -> hourly disaggregation) and a.rep == a.gap, 'summary', warm-up a
-// whole number of blocks: one row = one reporting step, and the binary64 fast form advances a
-// whole block at a time (smart_block_fast).
-template <typename R, int kVariant, int BLOCK, bool kSingle, bool kDaily>
+// kMode != kModeStep: the forcing arrays hold one row per block of a.rep steps (constant forcing
+// inside the block, the reference's daily -> hourly disaggregation), run and warm-up lengths are
+// whole numbers of blocks.  kModeBlock: one row = one reporting step, the fast form advances a
+// whole block at a time (smart_block_fast).  kModeBlockSub: reports fall inside the block.
+template <typename R, int kVariant, int BLOCK, bool kSingle, int kMode>
 __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
                                              const FastPar<R> &fp_, const Smem<R, BLOCK> &sm, long long m, bool active,
                                              int c, int col, int c_base, double area, double &gw_out, StepOut<R> &o)
 {
     constexpr bool kFast = kVariant == kVariantFast;
     constexpr bool kWide = sizeof(R) == 8;    // binary64 state: run-long sums stay in registers
+    constexpr bool kDaily = kMode != kModeStep;
     const int kc = kSingle ? 1 : a.kc;
     const int tile = stage_doubles(a.chunk, kc);
     const int tid = threadIdx.x;
@@ -219,7 +284,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     const int nWc = static_cast<int>((rowsW + chunk - 1) / chunk);
     const int nTot = nWc + static_cast<int>((rowsT + chunk - 1) / chunk);
     // with one simulation step per reporting step 'raw' and 'summary' coincide (structure.py:190-195)
-    const bool summary = kDaily || a.report_type == SMART_REPORT_SUMMARY || a.gap == 1;
+    const bool summary = kMode == kModeBlock || a.report_type == SMART_REPORT_SUMMARY || a.gap == 1;
 
     auto chunk_span = [&](int ci, long long &t0, int &n) {
         if (ci < nWc) {
@@ -339,7 +404,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         const double *fr = sm.rain + b * tile + col;
         const double *fp = sm.peva + b * tile + col;
         const double *tdp = sm.td + tid;      // T in binary64 (both modes), parked in shared memory
-        if (kDaily) {
+        if (kMode == kModeBlock) {
             const bool in_main = ci >= nWc;
             for (int i = 0; i < n; ++i) {
                 const double ex_d = __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]);   // structure.py:353-355
@@ -362,6 +427,72 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                     report(sval);
                 }
             }
+        } else if (kMode == kModeBlockSub) {
+            // reports inside the block: every hour hands its outflows to the reporting code below
+            const R scale = static_cast<R>(SCALE);           // (not yet set during the warm-up: unused there)
+            auto after_hour = [&](R q_riv, R q_gw, R q_all) {
+                acc += q_riv;
+                if (summary) {
+                    agw += q_gw;
+                    if (!kFast) aall += q_all;
+                }
+                if (--countdown == 0) {
+                    countdown = a.gap;
+                    const R sval = (summary ? acc : q_riv) * scale;             // structure.py:190 | :193
+                    if (summary) {
+                        if (kFast) {
+                            if (kWide) aall += acc;                             // fast form: aall = sum of Q_out
+                            else GD += static_cast<double>(acc);
+                        }
+                    } else {
+                        agw += q_gw;
+                        aall += q_all;
+                    }
+                    acc = R(0);
+                    report(sval);
+                }
+            };
+            for (int i = 0; i < n; ++i) {
+                const double rain_i = fr[0], peva_i = fp[0];
+                fr += kc;
+                fp += kc;
+                if constexpr (kFast) {
+                    const double ex_d = __dsub_rn(__dmul_rn(rain_i, *tdp), peva_i);   // structure.py:353-355
+                    const BlockPar<R> bp = block_par<R, BLOCK>(kconst);
+                    const R r_rk = kconst[6 * BLOCK];
+                    if (ex_d >= 0.0) {
+                        const R ex = static_cast<R>(ex_d);
+                        const R hex = fp_.Hz * ex;
+                        const unsigned mask = __activemask();
+                        if (kWide && !carry.valid) {
+                            carry.tot = soil_total(s);
+                            carry.valid = true;
+                        }
+#pragma unroll 2
+                        for (int h = 0; h < rep; ++h) {
+                            const R q_riv = s.riv * r_rk;
+                            R q_gw, q_in;
+                            fast_wet_hour<R, BLOCK>(s, fp_, kconst, bp, carry, ex, hex, mask, q_gw, q_in);
+                            after_hour(q_riv, q_gw, q_in);
+                        }
+                    } else {
+                        dry_block_soil<R>(s, kconst[0], ex_d, rep);
+                        carry.valid = false;
+#pragma unroll 2
+                        for (int h = 0; h < rep; ++h) {
+                            const R q_riv = s.riv * r_rk;
+                            R q_gw, q_in;
+                            fast_dry_hour<R, BLOCK>(s, fp_, kconst, bp, q_gw, q_in);
+                            after_hour(q_riv, q_gw, q_in);
+                        }
+                    }
+                } else {
+                    for (int h = 0; h < rep; ++h) {
+                        smart_step<R, true, kVariant == kVariantFluxes>(s, p, rain_i, peva_i, o);
+                        after_hour(o.q_riv, o.q_gw, o.q_all);
+                    }
+                }
+            }
         } else {
             // wet/dry driver of the fast step, formed one step ahead of the state
             double ex_next = kFast ? __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]) : 0.0;
@@ -381,7 +512,8 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                 acc += o.q_riv;
                 // groundwater share (structure.py:191, :194-195): 'summary' sums every step, 'raw'
                 // only the sampled ones.  Fast form: the pathway total is recovered from the river's
-                // mass balance (sum q_in = sum q_out + dV_river), so only sum q_out is accumulated.
+                // mass balance (sum q_in = sum q_out + dV_river), so only sum q_out is accumulated
+                // (binary64 state: in the otherwise unused register of the pathway total).
                 if (summary) {
                     agw += o.q_gw;
                     if (!kFast) aall += o.q_all;
@@ -390,7 +522,10 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                     countdown = a.gap;
                     const R sval = (summary ? acc : o.q_riv) * static_cast<R>(SCALE);   // structure.py:190 | :193
                     if (summary) {
-                        if (kFast) GD += static_cast<double>(acc);   // once per report step: shared memory
+                        if (kFast) {
+                            if (kWide) aall += acc;
+                            else GD += static_cast<double>(acc);    // once per report step: shared memory
+                        }
                     } else {
                         agw += o.q_gw;
                         aall += o.q_all;
@@ -404,7 +539,8 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     }
     double gn = kWide ? static_cast<double>(agw) : GN;
     double gd = kWide ? static_cast<double>(aall) : GD;
-    if (kFast && summary) gd = GD + (static_cast<double>(s.riv) - RIV0);
+    if (kFast && summary)   // sum of Q_out (block mode and binary32 state keep it in GD) + what the river gained
+        gd = ((kWide && kMode != kModeBlock) ? static_cast<double>(aall) : GD) + (static_cast<double>(s.riv) - RIV0);
     gw_out = gn / gd;
 }
 
@@ -444,7 +580,7 @@ __device__ __forceinline__ double write_member_results(const KArgs &a, const dou
                       : CUDART_NAN;                               // objfunctions.py:20-24
         if (a.scores != nullptr && active) {
 #pragma unroll
-            for (int k = 0; k < SMART_N_SCORES; ++k) a.scores[m * SMART_N_SCORES + k] = sc[k];
+            for (int k = 0; k < SMART_N_SCORES; ++k) a.scores[m * a.ld_s + k] = sc[k];
         }
         if (a.best_sign != 0 && active) {
             double t = sc[0];
@@ -454,7 +590,7 @@ __device__ __forceinline__ double write_member_results(const KArgs &a, const dou
             target = (t == t) ? t : -CUDART_INF;
         }
     }
-    if (a.gw != nullptr && active) a.gw[m] = gw;
+    if (a.gw != nullptr && active) a.gw[m * a.ld_g] = gw;
     return target;
 }
 
@@ -495,16 +631,7 @@ __device__ __forceinline__ void cta_best(const KArgs &a, double *scratch, double
     }
 }
 
-// The merged ("fast") form is exact only when no clamp, cap or leak predicate can fire:
-// every routing constant >= dt, inflows >= 0 (0 <= D <= 1, 0 <= H < 1), s' < 1.
-__device__ __forceinline__ bool fast_form_ok(const double *par, double dt)
-{
-    return par[6] * 3600.0 >= dt && par[7] * 3600.0 >= dt && par[8] * 3600.0 >= dt && par[9] * 3600.0 >= dt &&
-           par[4] >= 0.0 && par[4] <= 0.5 && par[5] > 0.0 && par[3] >= 0.0 && par[3] <= 1.0 && par[2] >= 0.0 &&
-           par[2] <= 0.99 && par[0] > 0.0;
-}
-
-template <typename R, int kVariant, int BLOCK, bool kSingle, bool kDaily>
+template <typename R, int kVariant, int BLOCK, bool kSingle, int kMode>
 __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
                                            long long m, bool active, int c, int col, int c_base, double area)
 {
@@ -544,7 +671,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         kconst[4 * BLOCK] = p.r_fk;
         kconst[5 * BLOCK] = p.r_gk;
         kconst[6 * BLOCK] = p.r_rk;
-        if (kDaily) {
+        if (kMode == kModeBlock) {
             // closed form of a dry block of a.rep steps (smart_block_fast): c_x^rep and
             // K_x = r_x * sum_{h<rep} c_w^(rep-1-h) c_x^h by Horner, no cancellation; binary64
             const double cx[3] = {1.0 - r_sk, 1.0 - r_fk, 1.0 - r_gk}, rx[3] = {r_sk, r_fk, r_gk};
@@ -599,7 +726,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 
     double gw = 0.0;
     StepOut<R> o;
-    run_timeline<R, kVariant, BLOCK, kSingle, kDaily>(a, s, p, fp_, sm, m, active, c, col, c_base, area, gw, o);
+    run_timeline<R, kVariant, BLOCK, kSingle, kMode>(a, s, p, fp_, sm, m, active, c, col, c_base, area, gw, o);
 
     // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
     const double target = write_member_results<BLOCK>(a, sm.acc + tid, m, active, c, gw);
@@ -629,19 +756,32 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 
 // Variant of the step a kernel instantiation carries.  The choice depends on the members'
 // parameters, which live on the device, so the host launches the fast kernel and the general
-// kernel back to back on the same stream: every CTA votes (one __syncthreads_or) on whether
-// all of its members qualify for the merged form and runs in exactly one of the two launches;
-// in the other it exits at once.  Separate kernels keep the fast variant's register count
-// (and so its occupancy) independent of the branch-faithful code.
-template <typename R, int kVariant, int BLOCK, int MAX_REGS, bool kSingle, bool kDaily>
+// kernel side by side (two streams, see launch()): every CTA votes (one __syncthreads_or) on
+// whether all of its members qualify for the merged form and runs in exactly one of the two
+// launches; in the other it exits at once.  Separate kernels keep the fast variant's register
+// count (and so its occupancy) independent of the branch-faithful code.  With a member_order from
+// smart_member_order() the members that need the branch-faithful form sit in CTAs of their own
+// (the order pads the fast group to a CTA boundary with idle threads), so no member's variant --
+// and therefore no member's bits -- depends on its neighbours.
+template <typename R, int kVariant, int BLOCK, int MAX_REGS, bool kSingle, int kMode>
 __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + tid;
-    const bool active = m_raw < a.N;
-    long long m = active ? m_raw : a.N - 1;         // tail threads shadow the last member, store nothing
-    if (a.order != nullptr) m = a.order[m];         // (single catchment, no [t][member] output: validate())
+    bool active = m_raw < a.n_threads;
+    long long m = active ? m_raw : a.n_threads - 1;   // tail threads shadow the last one, store nothing
+    if (a.order != nullptr) {
+        // (single catchment, no [t][member] output: validate().)  Idle slots hold -1; an idle thread
+        // shadows the member of its CTA's first thread, a CTA whose first slot is idle has no member.
+        const long long first = a.order[static_cast<long long>(blockIdx.x) * BLOCK];
+        if (first < 0) return;
+        m = a.order[m];
+        if (m < 0) {
+            active = false;
+            m = first;
+        }
+    }
 
     double par[SMART_N_PARAMS];
 #pragma unroll
@@ -669,7 +809,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         __syncthreads();
     }
 
-    run_member<R, kVariant, BLOCK, kSingle, kDaily>(a, smem_raw, par, m, active, c, col, c_base, area);
+    run_member<R, kVariant, BLOCK, kSingle, kMode>(a, smem_raw, par, m, active, c, col, c_base, area);
 }
 
 __global__ void best_finalize_kernel(const double *blk_score, const long long *blk_index, int n_blocks, int sign,
@@ -839,7 +979,19 @@ int block_of(const smart_batch_desc *d)
     return d->n_members <= 148LL * 736 * 8 ? kBlockSmall : kBlockLarge;
 }
 
-int n_blocks_of(const smart_batch_desc *d, int block) { return static_cast<int>((d->n_members + block - 1) / block); }
+// threads of a launch that may carry a member: one per member, or one per slot of member_order
+int64_t n_threads_of(const smart_batch_desc *d)
+{
+    return d->member_order && d->member_order_len > 0 ? d->member_order_len : d->n_members;
+}
+
+int n_blocks_of(const smart_batch_desc *d, int block) { return static_cast<int>((n_threads_of(d) + block - 1) / block); }
+
+int mode_of(const smart_batch_desc *d)
+{
+    if (d->forcing_repeat <= 1) return kModeStep;
+    return (d->report_gap == d->forcing_repeat && d->report_type == SMART_REPORT_SUMMARY) ? kModeBlock : kModeBlockSub;
+}
 
 int validate(const smart_batch_desc *d, bool host_mode = false)
 {
@@ -869,19 +1021,23 @@ int validate(const smart_batch_desc *d, bool host_mode = false)
             return fail(SMART_ERR_GAP, "cannot reshape the warm-up run into (-1, report_gap)");
     }
     if (d->forcing_repeat > 1) {
-        // block-constant forcing: only the configuration the reference's disaggregation produces
+        // block-constant forcing (what the reference's disaggregation produces): whole blocks only,
+        // reports at the end of a block or at equal distances inside it
         if (d->n_steps % d->forcing_repeat != 0 || d->n_warmup % d->forcing_repeat != 0 ||
-            d->report_gap != d->forcing_repeat || d->report_type != SMART_REPORT_SUMMARY || d->initial_state ||
-            d->last_state)
+            d->forcing_repeat % d->report_gap != 0 || d->initial_state || d->last_state)
             return fail(SMART_ERR_BAD_ARG,
-                        "forcing_repeat > 1 needs report_gap == forcing_repeat, 'summary' reporting, run and warm-up "
-                        "lengths that are multiples of it, and no initial_state/last_state");
+                        "forcing_repeat > 1 needs a report_gap that divides it, run and warm-up lengths that are "
+                        "multiples of it, and no initial_state/last_state");
     }
     if (d->discharge && d->ld_discharge < d->n_members)
         return fail(SMART_ERR_BAD_ARG, "ld_discharge must be >= n_members");
     if (d->member_order && (d->n_catchments != 1 || d->discharge || d->last_state || d->initial_state || host_mode))
         return fail(SMART_ERR_BAD_ARG,
                     "member_order needs one catchment, device pointers and no discharge/last_state/initial_state");
+    if (d->member_order && d->member_order_len != 0 && d->member_order_len < d->n_members)
+        return fail(SMART_ERR_BAD_ARG, "member_order_len must be 0 (= n_members) or >= n_members");
+    if ((d->scores && d->ld_scores != 0 && d->ld_scores < SMART_N_SCORES) || (d->gw && d->ld_gw < 0))
+        return fail(SMART_ERR_BAD_ARG, "ld_scores must be 0 (= 8) or >= 8, ld_gw 0 (= 1) or >= 1");
     if (d->best_sign != 0) {
         if (!d->obs || (!d->workspace && !host_mode))
             return fail(SMART_ERR_BAD_ARG, "best member needs obs and workspace");
@@ -910,6 +1066,9 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     a.gw = d->gw;
     a.last_state = d->last_state;
     a.N = d->n_members;
+    a.n_threads = n_threads_of(d);
+    a.ld_s = d->ld_scores > 0 ? d->ld_scores : SMART_N_SCORES;
+    a.ld_g = d->ld_gw > 0 ? d->ld_gw : 1;
     a.T = d->n_steps;
     a.W = d->initial_state ? 0 : d->n_warmup;
     a.ld_q = d->ld_discharge;
@@ -932,7 +1091,9 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
 
     const int block = block_of(d);
     const int blocks = n_blocks_of(d, block);
-    const bool daily = d->forcing_repeat > 1;
+    const int mode = mode_of(d);
+    const bool daily = mode != kModeStep;
+    a.mode = mode;
     a.rep = daily ? d->forcing_repeat : 1;
     if (a.C == 1) {
         a.kc = 1;
@@ -955,13 +1116,15 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
     const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(stage_doubles(a.chunk, a.kc)) + kAccSlots * block) +
-                        sizeof(R) * (kConstSlots + 1) * block + sizeof(double) * (1 + (daily ? kBlockSlots : 0)) * block;
+                        sizeof(R) * (kConstSlots + 1) * block +
+                        sizeof(double) * (1 + (mode == kModeBlock ? kBlockSlots : 0)) * block;
     using Kernel = void (*)(const KArgs);
-    auto go = [&](Kernel kernel) -> int {
+    auto go = [&](Kernel kernel, cudaStream_t st) -> int {
         if (smem > 48 * 1024)   // above the default dynamic shared memory limit: opt in per kernel
             SMART_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<blocks, block, smem, stream>>>(a);
+        kernel<<<blocks, block, smem, st>>>(a);
         SMART_CUDA(cudaGetLastError());
+        count_launches(1);
         return SMART_OK;
     };
     // Fast kernel: two register budgets are compiled.  The roomy one (no spills) is quicker per
@@ -970,73 +1133,85 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     constexpr int kLeanRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64_LEAN : SMART_FAST_REGS_F32;
     constexpr int kRoomyRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64 : SMART_FAST_REGS_F32;
     constexpr int kSlowRegs = SMART_SLOW_REGS;
-    Kernel fast_lean, fast_roomy, general, fluxes;
-    auto pick = [&](auto block_tag, auto single_tag, auto daily_tag) {
+    Kernel fast_lean = nullptr, fast_roomy = nullptr, general = nullptr, fluxes = nullptr;
+    auto pick = [&](auto block_tag, auto single_tag, auto mode_tag) {
         constexpr int B = decltype(block_tag)::value;
         constexpr bool S = decltype(single_tag)::value;
-        constexpr bool D = decltype(daily_tag)::value;
-        fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S, D>;
-        fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S, D>;
-        general = smart_batch_kernel<R, kVariantGeneral, B, kSlowRegs, S, D>;
-        fluxes = smart_batch_kernel<R, kVariantFluxes, B, kSlowRegs, S, false>;
+        constexpr int M = decltype(mode_tag)::value;
+        fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S, M>;
+        fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S, M>;
+        general = smart_batch_kernel<R, kVariantGeneral, B, kSlowRegs, S, M>;
+        fluxes = smart_batch_kernel<R, kVariantFluxes, B, kSlowRegs, S, kModeStep>;
+    };
+    auto pick_mode = [&](auto block_tag, auto single_tag) {
+        if (mode == kModeStep) pick(block_tag, single_tag, std::integral_constant<int, kModeStep>{});
+        else if (mode == kModeBlock) pick(block_tag, single_tag, std::integral_constant<int, kModeBlock>{});
+        else pick(block_tag, single_tag, std::integral_constant<int, kModeBlockSub>{});
     };
     using BL = std::integral_constant<int, kBlockLarge>;
     using BS = std::integral_constant<int, kBlockSmall>;
-    using Yes = std::true_type;
-    using No = std::false_type;
-    const int sel = (block == kBlockLarge ? 4 : 0) | (a.C == 1 ? 2 : 0) | (daily ? 1 : 0);
-    switch (sel) {
-        case 0: pick(BS{}, No{}, No{}); break;
-        case 1: pick(BS{}, No{}, Yes{}); break;
-        case 2: pick(BS{}, Yes{}, No{}); break;
-        case 3: pick(BS{}, Yes{}, Yes{}); break;
-        case 4: pick(BL{}, No{}, No{}); break;
-        case 5: pick(BL{}, No{}, Yes{}); break;
-        case 6: pick(BL{}, Yes{}, No{}); break;
-        default: pick(BL{}, Yes{}, Yes{}); break;
+    switch ((block == kBlockLarge ? 2 : 0) | (a.C == 1 ? 1 : 0)) {
+        case 0: pick_mode(BS{}, std::false_type{}); break;
+        case 1: pick_mode(BS{}, std::true_type{}); break;
+        case 2: pick_mode(BL{}, std::false_type{}); break;
+        default: pick_mode(BL{}, std::true_type{}); break;
     }
     if (d->last_state) {
-        if ((rc = go(fluxes))) return rc;
+        if ((rc = go(fluxes, stream))) return rc;
+    } else if (a.force_general || d->initial_state) {
+        if ((rc = go(general, stream))) return rc;
     } else {
-        if (!a.force_general && !d->initial_state) {
-            Kernel fast = fast_roomy;
-            if (fast_lean != fast_roomy) {
-                int dev = 0, sms = 0, per_sm_lean = 0, per_sm_roomy = 0;
-                SMART_CUDA(cudaGetDevice(&dev));
-                SMART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-                SMART_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lean, fast_lean, block, smem));
-                SMART_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_roomy, fast_roomy, block, smem));
-                // cost model: full waves at the measured steady rates (lean is ~6 % slower per
-                // member), a ragged last wave costs at least 40 % of a full one (latency bound)
-                auto cost = [&](int per_sm, double rate) {
-                    const double slots = static_cast<double>(per_sm) * sms;
-                    const double waves = blocks / slots;
-                    const double whole = floor(waves), frac = waves - whole;
-                    const double tail = frac == 0.0 ? 0.0 : (frac > 0.4 ? frac : 0.4);
-                    return (whole + (whole == 0.0 ? frac : tail)) * slots / rate;
-                };
-                if (per_sm_lean > 0 && per_sm_roomy > 0 && cost(per_sm_lean, 0.94) < cost(per_sm_roomy, 1.0))
-                    fast = fast_lean;
-            }
-            if ((rc = go(fast))) return rc;
+        Kernel fast = fast_roomy;
+        if (fast_lean != fast_roomy) {
+            int dev = 0, sms = 0, per_sm_lean = 0, per_sm_roomy = 0;
+            SMART_CUDA(cudaGetDevice(&dev));
+            SMART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            SMART_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lean, fast_lean, block, smem));
+            SMART_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_roomy, fast_roomy, block, smem));
+            // cost model: full waves at the measured steady rates (lean is ~6 % slower per
+            // member), a ragged last wave costs at least 40 % of a full one (latency bound)
+            auto cost = [&](int per_sm, double rate) {
+                const double slots = static_cast<double>(per_sm) * sms;
+                const double waves = blocks / slots;
+                const double whole = floor(waves), frac = waves - whole;
+                const double tail = frac == 0.0 ? 0.0 : (frac > 0.4 ? frac : 0.4);
+                return (whole + (whole == 0.0 ? frac : tail)) * slots / rate;
+            };
+            if (per_sm_lean > 0 && per_sm_roomy > 0 && cost(per_sm_lean, kLeanRate) < cost(per_sm_roomy, 1.0))
+                fast = fast_lean;
+            static const int forced = [] {
+                const char *e = getenv("SMART_B200_FAST_REGS");   // kernel tuning: "lean" | "roomy"
+                return e ? (e[0] == 'l' ? 1 : 2) : 0;
+            }();
+            if (forced) fast = forced == 1 ? fast_lean : fast_roomy;
         }
-        if ((rc = go(general))) return rc;
+        // The two forms side by side: the branch-faithful kernel goes to a stream of its own
+        // (forked from and joined back into the caller's, so the call stays stream-ordered) and
+        // its CTAs share the SMs with the fast kernel's instead of queueing behind the whole fast
+        // launch -- members outside the fast form's domain are then paid for by their own work,
+        // not by a second pass of the timeline at a few CTAs' worth of occupancy.
+        SideStream *side = side_stream();
+        if (side != nullptr) {
+            std::lock_guard<std::mutex> hold(side->mu);
+            SMART_CUDA(cudaEventRecord(side->fork, stream));
+            SMART_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+            if ((rc = go(general, side->stream))) return rc;
+            SMART_CUDA(cudaEventRecord(side->join, side->stream));
+            if ((rc = go(fast, stream))) return rc;
+            SMART_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
+        } else {
+            if ((rc = go(fast, stream))) return rc;
+            if ((rc = go(general, stream))) return rc;
+        }
     }
     if (d->best_sign != 0) {
         best_finalize_kernel<<<1, 32, 0, stream>>>(a.blk_best_score, a.blk_best_index, blocks, d->best_sign,
                                                    d->best_score, reinterpret_cast<long long *>(d->best_index));
         SMART_CUDA(cudaGetLastError());
+        count_launches(1);
     }
     return SMART_OK;
 }
-
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf()
-    {
-        if (p) cudaFree(p);
-    }
-};
 
 }  // namespace
 
@@ -1048,11 +1223,15 @@ extern "C" int smart_batch_run_f32(const smart_batch_desc *d, void *stream)
 #else
 // error channel shared with smart_kernels_f32.cu, smart_select.cu and smart_sample.cu
 int smart_internal_fail(int code, const char *msg) { return fail(code, msg); }
+void smart_internal_count(int n) { count_launches(n); }
+void *smart_internal_side_stream() { return side_stream_impl(); }
 
 // =================================================================== C ABI
 extern "C" {
 
 int smart_version(void) { return SMART_B200_VERSION; }
+
+int64_t smart_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char *smart_last_error(void) { return g_err.c_str(); }
 
@@ -1070,6 +1249,7 @@ int smart_obs_stats(const double *obs, int64_t n_report, int32_t n_catchments, d
         return fail(SMART_ERR_BAD_ARG, "smart_obs_stats: bad argument");
     obs_stats_kernel<<<n_catchments, 256, 0, static_cast<cudaStream_t>(stream)>>>(obs, n_report, n_catchments, stats);
     SMART_CUDA(cudaGetLastError());
+    count_launches(1);
     return SMART_OK;
 }
 
@@ -1090,6 +1270,7 @@ static int stamp_rows(const double *in, int64_t n_in, int32_t n_catchments, int3
     disaggregate_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(in, n_in, n_catchments, repeat, div,
                                                                                    out);
     SMART_CUDA(cudaGetLastError());
+    count_launches(1);
     return SMART_OK;
 }
 
@@ -1132,6 +1313,42 @@ int smart_score_discharge(const void *discharge, int64_t ld_discharge, int64_t n
     else
         return fail(SMART_ERR_BAD_ARG, "precision must be 64 or 32");
     SMART_CUDA(cudaGetLastError());
+    count_launches(1);
+    return SMART_OK;
+}
+
+// Device arena of the *_host entry points: one grow-only allocation and one stream per host thread
+// and device, reused from call to call (a per-call cudaMalloc/cudaFree pair costs more than a small
+// batch does).  smart_host_arena_release() gives the memory back.
+namespace {
+struct HostArena {
+    int device = -1;
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    cudaStream_t stream = nullptr;
+    void release()
+    {
+        if (base) cudaFree(base);
+        if (stream) cudaStreamDestroy(stream);
+        base = nullptr;
+        stream = nullptr;
+        cap = used = 0;
+        device = -1;
+    }
+    ~HostArena() {}   // (process exit: the CUDA context may already be gone; nothing to do)
+    void *take(size_t bytes)
+    {
+        void *p = base + used;
+        used += (bytes + 255) & ~static_cast<size_t>(255);
+        return p;
+    }
+};
+thread_local HostArena g_arena;
+}  // namespace
+
+int smart_host_arena_release(void)
+{
+    g_arena.release();
     return SMART_OK;
 }
 
@@ -1144,79 +1361,104 @@ int smart_batch_run_host(const smart_batch_desc *h, int precision, int device)
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev < 1)
         return fail(SMART_ERR_NO_DEVICE, "no CUDA device: the SMART hot path has no CPU fallback");
     SMART_CUDA(cudaSetDevice(device));
-    cudaStream_t st;
-    SMART_CUDA(cudaStreamCreate(&st));
-    struct StreamGuard {
-        cudaStream_t s;
-        ~StreamGuard() { cudaStreamDestroy(s); }
-    } guard{st};
 
     const int64_t N = h->n_members, T = h->n_steps, C = h->n_catchments;
     const int64_t n_rep = n_report_of(h);
     const size_t q_elem = precision == 64 ? sizeof(double) : sizeof(float);
+    const int64_t rows = h->forcing_repeat > 1 ? T / h->forcing_repeat : T;   // one row per block of steps
+    const size_t b_params = sizeof(double) * N * SMART_N_PARAMS, b_forcing = sizeof(double) * rows * C;
+    const size_t b_area = sizeof(double) * C, b_init = h->initial_state ? sizeof(double) * N * SMART_N_VARS : 0;
+    const size_t b_obs = h->obs ? sizeof(double) * n_rep * C : 0, b_stats = h->obs ? sizeof(double) * C * SMART_OBS_STATS : 0;
+    const size_t b_q = h->discharge ? q_elem * n_rep * N : 0, b_scores = h->scores ? sizeof(double) * N * SMART_N_SCORES : 0;
+    const size_t b_gw = h->gw ? sizeof(double) * N : 0, b_last = h->last_state ? sizeof(double) * N * SMART_N_VARS : 0;
+    const size_t b_ws = h->best_sign != 0 ? smart_batch_workspace_bytes(h) + 16 : 0;
+    const size_t sizes[] = {b_params, b_forcing, b_forcing, b_area, b_init, b_obs, b_stats, b_q, b_scores, b_gw, b_last, b_ws};
+    size_t need = 0;
+    for (size_t b : sizes) need += (b + 255) & ~static_cast<size_t>(255);
+
+    HostArena &ar = g_arena;
+    if (ar.device != device) {
+        ar.release();
+        ar.device = device;
+    }
+    if (ar.stream == nullptr) SMART_CUDA(cudaStreamCreateWithFlags(&ar.stream, cudaStreamNonBlocking));
+    if (ar.cap < need) {
+        if (ar.base) SMART_CUDA(cudaFree(ar.base));
+        ar.base = nullptr;
+        ar.cap = 0;
+        const size_t grow = need + need / 4;          // head room: the next, slightly larger batch fits too
+        SMART_CUDA(cudaMalloc(reinterpret_cast<void **>(&ar.base), grow));
+        ar.cap = grow;
+    }
+    ar.used = 0;
+    cudaStream_t st = ar.stream;
+
     smart_batch_desc d = *h;
-    DevBuf params, rain, peva, area, obs, stats, init, q, scores, gw, last, ws, bs, bi;
-    auto up = [&](DevBuf &b, const void *src, size_t bytes, const void **dst) -> int {
-        SMART_CUDA(cudaMalloc(&b.p, bytes));
-        SMART_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
-        *dst = b.p;
+    auto up = [&](const void *src, size_t bytes, const void **dst) -> int {
+        void *p = ar.take(bytes);
+        SMART_CUDA(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, st));
+        *dst = p;
         return SMART_OK;
     };
-    if ((rc = up(params, h->params, sizeof(double) * N * SMART_N_PARAMS, (const void **)&d.params))) return rc;
-    const int64_t rows = h->forcing_repeat > 1 ? T / h->forcing_repeat : T;   // one row per block of steps
-    if ((rc = up(rain, h->rain, sizeof(double) * rows * C, (const void **)&d.rain))) return rc;
-    if ((rc = up(peva, h->peva, sizeof(double) * rows * C, (const void **)&d.peva))) return rc;
-    if ((rc = up(area, h->area_m2, sizeof(double) * C, (const void **)&d.area_m2))) return rc;
-    if (h->initial_state &&
-        (rc = up(init, h->initial_state, sizeof(double) * N * SMART_N_VARS, (const void **)&d.initial_state)))
-        return rc;
+    if ((rc = up(h->params, b_params, (const void **)&d.params))) return rc;
+    if ((rc = up(h->rain, b_forcing, (const void **)&d.rain))) return rc;
+    if ((rc = up(h->peva, b_forcing, (const void **)&d.peva))) return rc;
+    if ((rc = up(h->area_m2, b_area, (const void **)&d.area_m2))) return rc;
+    if (h->initial_state && (rc = up(h->initial_state, b_init, (const void **)&d.initial_state))) return rc;
     if (h->obs) {
-        if ((rc = up(obs, h->obs, sizeof(double) * n_rep * C, (const void **)&d.obs))) return rc;
-        SMART_CUDA(cudaMalloc(&stats.p, sizeof(double) * C * SMART_OBS_STATS));
-        d.obs_stats = static_cast<double *>(stats.p);
-        if ((rc = smart_obs_stats(d.obs, n_rep, static_cast<int32_t>(C), static_cast<double *>(stats.p), st)))
-            return rc;
+        if ((rc = up(h->obs, b_obs, (const void **)&d.obs))) return rc;
+        double *stats = static_cast<double *>(ar.take(b_stats));
+        d.obs_stats = stats;
+        if ((rc = smart_obs_stats(d.obs, n_rep, static_cast<int32_t>(C), stats, st))) return rc;
     }
+    void *q = nullptr;
     if (h->discharge) {
         d.ld_discharge = N;
-        SMART_CUDA(cudaMalloc(&q.p, q_elem * n_rep * N));
-        d.discharge = q.p;
+        d.discharge = q = ar.take(b_q);
     }
     if (h->scores) {
-        SMART_CUDA(cudaMalloc(&scores.p, sizeof(double) * N * SMART_N_SCORES));
-        d.scores = static_cast<double *>(scores.p);
+        d.scores = static_cast<double *>(ar.take(b_scores));
+        d.ld_scores = SMART_N_SCORES;
     }
     if (h->gw) {
-        SMART_CUDA(cudaMalloc(&gw.p, sizeof(double) * N));
-        d.gw = static_cast<double *>(gw.p);
+        d.gw = static_cast<double *>(ar.take(b_gw));
+        d.ld_gw = 1;
     }
-    if (h->last_state) {
-        SMART_CUDA(cudaMalloc(&last.p, sizeof(double) * N * SMART_N_VARS));
-        d.last_state = static_cast<double *>(last.p);
-    }
+    if (h->last_state) d.last_state = static_cast<double *>(ar.take(b_last));
     if (h->best_sign != 0) {
-        SMART_CUDA(cudaMalloc(&ws.p, smart_batch_workspace_bytes(h)));
-        SMART_CUDA(cudaMalloc(&bs.p, sizeof(double)));
-        SMART_CUDA(cudaMalloc(&bi.p, sizeof(long long)));
-        d.workspace = ws.p;
-        d.best_score = static_cast<double *>(bs.p);
-        d.best_index = static_cast<int64_t *>(bi.p);
+        char *ws = static_cast<char *>(ar.take(b_ws));
+        d.best_score = reinterpret_cast<double *>(ws);
+        d.best_index = reinterpret_cast<int64_t *>(ws + 8);
+        d.workspace = ws + 16;
     }
     rc = precision == 64 ? launch<double>(&d, st) : smart_batch_run_f32(&d, st);
     if (rc) return rc;
     if (h->discharge) {
         // host layout keeps the caller's leading dimension
-        SMART_CUDA(cudaMemcpy2DAsync(h->discharge, q_elem * h->ld_discharge, q.p, q_elem * N, q_elem * N, n_rep,
+        SMART_CUDA(cudaMemcpy2DAsync(h->discharge, q_elem * h->ld_discharge, q, q_elem * N, q_elem * N, n_rep,
                                      cudaMemcpyDeviceToHost, st));
     }
-    if (h->scores)
-        SMART_CUDA(cudaMemcpyAsync(h->scores, scores.p, sizeof(double) * N * SMART_N_SCORES, cudaMemcpyDeviceToHost, st));
-    if (h->gw) SMART_CUDA(cudaMemcpyAsync(h->gw, gw.p, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+    if (h->scores) {
+        const int64_t ld = h->ld_scores > 0 ? h->ld_scores : SMART_N_SCORES;
+        if (ld == SMART_N_SCORES)
+            SMART_CUDA(cudaMemcpyAsync(h->scores, d.scores, b_scores, cudaMemcpyDeviceToHost, st));
+        else
+            SMART_CUDA(cudaMemcpy2DAsync(h->scores, sizeof(double) * ld, d.scores, sizeof(double) * SMART_N_SCORES,
+                                         sizeof(double) * SMART_N_SCORES, N, cudaMemcpyDeviceToHost, st));
+    }
+    if (h->gw) {
+        const int64_t ld = h->ld_gw > 0 ? h->ld_gw : 1;
+        if (ld == 1)
+            SMART_CUDA(cudaMemcpyAsync(h->gw, d.gw, b_gw, cudaMemcpyDeviceToHost, st));
+        else
+            SMART_CUDA(cudaMemcpy2DAsync(h->gw, sizeof(double) * ld, d.gw, sizeof(double), sizeof(double), N,
+                                         cudaMemcpyDeviceToHost, st));
+    }
     if (h->last_state)
-        SMART_CUDA(cudaMemcpyAsync(h->last_state, last.p, sizeof(double) * N * SMART_N_VARS, cudaMemcpyDeviceToHost, st));
+        SMART_CUDA(cudaMemcpyAsync(h->last_state, d.last_state, b_last, cudaMemcpyDeviceToHost, st));
     if (h->best_sign != 0) {
-        if (h->best_score) SMART_CUDA(cudaMemcpyAsync(h->best_score, bs.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (h->best_index) SMART_CUDA(cudaMemcpyAsync(h->best_index, bi.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        if (h->best_score) SMART_CUDA(cudaMemcpyAsync(h->best_score, d.best_score, sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (h->best_index) SMART_CUDA(cudaMemcpyAsync(h->best_index, d.best_index, sizeof(long long), cudaMemcpyDeviceToHost, st));
     }
     SMART_CUDA(cudaStreamSynchronize(st));
     return SMART_OK;
@@ -1262,6 +1504,7 @@ int smart_fma_peak_probe(int precision, int blocks, int threads, int64_t iters, 
     else
         return fail(SMART_ERR_BAD_ARG, "precision must be 64 or 32");
     SMART_CUDA(cudaGetLastError());
+    count_launches(1);
     return SMART_OK;
 }
 

@@ -21,6 +21,7 @@
 #include "smart_b200.h"
 
 int smart_internal_fail(int code, const char *msg);     // smart_kernels.cu
+void smart_internal_count(int n);                       // smart_kernels.cu (smart_launch_count)
 
 namespace {
 
@@ -100,5 +101,6 @@ extern "C" int smart_lhs_rows(uint64_t seed, int64_t n_total, int64_t row_first,
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return smart_internal_fail(SMART_ERR_CUDA, (std::string("smart_lhs_rows: ") + cudaGetErrorString(e)).c_str());
+    smart_internal_count(1);
     return SMART_OK;
 }

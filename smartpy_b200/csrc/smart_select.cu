@@ -19,8 +19,10 @@
 #include <string>
 
 #include "smart_b200.h"
+#include "smart_step.cuh"
 
 int smart_internal_fail(int code, const char *msg);     // smart_kernels.cu (sets smart_last_error)
+void smart_internal_count(int n);                       // smart_kernels.cu (smart_launch_count)
 
 namespace {
 
@@ -329,6 +331,149 @@ __global__ void emit_rows_kernel(const unsigned int *__restrict__ cand_row, long
     if (i == 0 && kept_out) *kept_out = (long long)st->kept;
 }
 
+// ascending bitonic sort of `padded` (a power of two) (key, row) pairs: 2048-pair chunks in shared
+// memory, global steps only for distances >= 2048
+void sort_pairs(unsigned long long *cand_key, unsigned int *cand_row, long long padded, cudaStream_t s)
+{
+    const int chunk = (int)(padded < kSortChunk ? padded : kSortChunk);
+    if (padded <= 1) return;
+    const unsigned n_chunks = (unsigned)(padded / chunk);
+    const int threads = chunk / 2 < 32 ? 32 : chunk / 2;
+    int launches = 1;
+    bitonic_shared_kernel<<<n_chunks, threads, 0, s>>>(cand_key, cand_row, chunk, 2, chunk);
+    for (long long kk = 2ll * chunk; kk <= padded; kk <<= 1) {
+        for (long long j = kk >> 1; j >= chunk; j >>= 1) {
+            bitonic_global_kernel<<<(unsigned)((padded / 2 + 255) / 256), 256, 0, s>>>(cand_key, cand_row, padded / 2, j, kk);
+            ++launches;
+        }
+        bitonic_shared_kernel<<<n_chunks, threads, 0, s>>>(cand_key, cand_row, chunk, kk, kk);
+        ++launches;
+    }
+    smart_internal_count(launches);
+}
+
+// ------------------------------------------------------------------ grouping of the members of a launch
+constexpr int kOrderPad = 128;            // the largest CTA of the step kernel: groups start on its multiples
+constexpr double kOrderTSlices = 64.0;    // slices of the T range inside which members are ordered by S * Z
+
+struct OrderState {
+    unsigned long long t_min, t_max, x_min, x_max;   // ordered_key images (monotonic in the value)
+    unsigned int n_fast;
+};
+
+__device__ __forceinline__ double key_to_double(unsigned long long k)
+{
+    const unsigned long long u = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+__global__ void order_init_kernel(OrderState *st)
+{
+    st->t_min = st->x_min = ~0ull;
+    st->t_max = st->x_max = 0ull;
+    st->n_fast = 0;
+}
+
+// range of T and of S * Z over the batch, number of members inside the fast form's domain
+__global__ void __launch_bounds__(256)
+order_range_kernel(const double *__restrict__ params, long long n, double dt, OrderState *st)
+{
+    unsigned long long tmin = ~0ull, tmax = 0ull, xmin = ~0ull, xmax = 0ull;
+    unsigned int n_fast = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double par[SMART_N_PARAMS];
+#pragma unroll
+        for (int k = 0; k < SMART_N_PARAMS; ++k) par[k] = params[i * SMART_N_PARAMS + k];
+        const unsigned long long t = ordered_key(par[0]), x = ordered_key(par[4] * par[5]);
+        tmin = t < tmin ? t : tmin;
+        tmax = t > tmax ? t : tmax;
+        xmin = x < xmin ? x : xmin;
+        xmax = x > xmax ? x : xmax;
+        n_fast += smart::fast_form_ok(par, dt) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, tmin, off), b = __shfl_xor_sync(0xffffffffu, tmax, off);
+        const unsigned long long c = __shfl_xor_sync(0xffffffffu, xmin, off), d = __shfl_xor_sync(0xffffffffu, xmax, off);
+        tmin = a < tmin ? a : tmin;
+        tmax = b > tmax ? b : tmax;
+        xmin = c < xmin ? c : xmin;
+        xmax = d > xmax ? d : xmax;
+    }
+    n_fast = __reduce_add_sync(0xffffffffu, n_fast);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&st->t_min, tmin);
+        atomicMax(&st->t_max, tmax);
+        atomicMin(&st->x_min, xmin);
+        atomicMax(&st->x_max, xmax);
+        if (n_fast) atomicAdd(&st->n_fast, n_fast);
+    }
+}
+
+// key = [needs the branch-faithful form] * 2 * slices + slice of T + S * Z scaled into [0, 1)
+__global__ void __launch_bounds__(256)
+order_keys_kernel(const double *__restrict__ params, long long n, long long padded, double dt, const OrderState *st,
+                  unsigned long long *__restrict__ cand_key, unsigned int *__restrict__ cand_row)
+{
+    const double tmin = key_to_double(st->t_min), tmax = key_to_double(st->t_max);
+    const double xmin = key_to_double(st->x_min), xmax = key_to_double(st->x_max);
+    const double tw = tmax - tmin + 1e-300, xw = xmax - xmin + 1e-300;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += (long long)gridDim.x * blockDim.x) {
+        if (i >= n) {
+            cand_key[i] = ~0ull;
+            cand_row[i] = kPadRow;
+            continue;
+        }
+        double par[SMART_N_PARAMS];
+#pragma unroll
+        for (int k = 0; k < SMART_N_PARAMS; ++k) par[k] = params[i * SMART_N_PARAMS + k];
+        double slice = floor((par[0] - tmin) / tw * kOrderTSlices);
+        slice = slice < kOrderTSlices - 1.0 ? slice : kOrderTSlices - 1.0;
+        if (!(slice >= 0.0)) slice = 0.0;                       // NaN parameters: anywhere, but somewhere
+        double frac = (par[4] * par[5] - xmin) / xw * 0.999;
+        if (!(frac >= 0.0)) frac = 0.0;
+        const double group = smart::fast_form_ok(par, dt) ? 0.0 : 2.0 * kOrderTSlices;
+        cand_key[i] = ordered_key(group + slice + frac);
+        cand_row[i] = (unsigned int)i;
+    }
+}
+
+// sorted rows -> slots: fast members at [0, F), idle slots up to the next multiple of kOrderPad,
+// then the members of the branch-faithful form, idle slots to the end
+__global__ void __launch_bounds__(256)
+order_emit_kernel(const unsigned int *__restrict__ cand_row, long long n, long long slots, const OrderState *st,
+                  long long *__restrict__ order_out)
+{
+    const long long n_fast = st->n_fast;
+    const long long general_at = (n_fast + kOrderPad - 1) / kOrderPad * kOrderPad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (long long)gridDim.x * blockDim.x) {
+        long long src = -1;
+        if (i < n_fast) src = i;
+        else if (i >= general_at && i - general_at < n - n_fast) src = n_fast + (i - general_at);
+        order_out[i] = src < 0 ? -1 : (long long)cand_row[src];
+    }
+}
+
+// ------------------------------------------------------------------ block-constant forcing
+__global__ void __launch_bounds__(256)
+fold_blocks_kernel(const double *__restrict__ rows, long long n_blocks, int C, int k, double *__restrict__ out, int *flag)
+{
+    bool same = true;
+    const long long total = n_blocks * C;
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < total; j += (long long)gridDim.x * blockDim.x) {
+        const long long b = j / C;
+        const int c = (int)(j - b * C);
+        const double *p = rows + (b * k) * (long long)C + c;
+        const unsigned long long first = (unsigned long long)__double_as_longlong(p[0]);
+        for (int h = 1; h < k; ++h)     // bit equality: what an equal split of one value produces
+            same = same && ((unsigned long long)__double_as_longlong(p[(long long)h * C]) == first);
+        out[j] = p[0];
+    }
+    if (!__all_sync(0xffffffffu, same) && (threadIdx.x & 31) == 0) atomicExch(flag, 0);
+}
+
+__global__ void set_flag_kernel(int *flag, int v) { *flag = v; }
+
 long long pow2_at_least(long long k)
 {
     long long p = 1;
@@ -406,6 +551,7 @@ int smart_condition_rows(const double *scores, int64_t n_rows, int32_t ld, const
     scan_counts_kernel<<<1, 1024, 0, s>>>(blk_count, blk_offset, n_blk, (long long *)count_out);
     scatter_rows_kernel<<<(unsigned)n_blk, kRowBlock, 0, s>>>(scores, n_rows, ld, c, blk_offset, (long long *)rows_out);
     SEL_CUDA(cudaGetLastError());
+    smart_internal_count(3);
     return SMART_OK;
 }
 
@@ -442,19 +588,62 @@ int smart_best_rows(const double *scores, int64_t n_rows, int32_t ld, int32_t ta
     gather_best_kernel<<<grid, 256, 0, s>>>(keys, n_rows, st, cand_key, cand_row, k);
     if (padded > k)
         pad_candidates_kernel<<<(unsigned)((padded - k + 255) / 256), 256, 0, s>>>(cand_key, cand_row, k, padded);
+    smart_internal_count(2 + 24 + 1 + (padded > k ? 1 : 0) + 1);      // init, keys, 12 x (histogram, pick), gather, pad, emit
 
-    const int chunk = (int)(padded < kSortChunk ? padded : kSortChunk);
-    if (padded > 1) {
-        const unsigned n_chunks = (unsigned)(padded / chunk);
-        const int threads = chunk / 2 < 32 ? 32 : chunk / 2;
-        bitonic_shared_kernel<<<n_chunks, threads, 0, s>>>(cand_key, cand_row, chunk, 2, chunk);
-        for (long long kk = 2ll * chunk; kk <= padded; kk <<= 1) {
-            for (long long j = kk >> 1; j >= chunk; j >>= 1)
-                bitonic_global_kernel<<<(unsigned)((padded / 2 + 255) / 256), 256, 0, s>>>(cand_key, cand_row, padded / 2, j, kk);
-            bitonic_shared_kernel<<<n_chunks, threads, 0, s>>>(cand_key, cand_row, chunk, kk, kk);
-        }
-    }
+    sort_pairs(cand_key, cand_row, padded, s);
     emit_rows_kernel<<<(unsigned)((k + 255) / 256), 256, 0, s>>>(cand_row, k, st, (long long *)rows_out, (long long *)kept_out);
+    SEL_CUDA(cudaGetLastError());
+    return SMART_OK;
+}
+
+int64_t smart_member_order_len(int64_t n_members)
+{
+    if (n_members < 0) n_members = 0;
+    // the fast group rounded up to a CTA boundary + the other group: at most one padding run
+    return (n_members + kOrderPad - 1) / kOrderPad * kOrderPad + kOrderPad;
+}
+
+size_t smart_member_order_workspace_bytes(int64_t n_members)
+{
+    const size_t padded = (size_t)pow2_at_least(n_members > 0 ? n_members : 1);
+    return align256(sizeof(OrderState)) + align256(padded * 8) + align256(padded * 4);
+}
+
+int smart_member_order(const double *params, int64_t n_members, double dt_sec, int64_t *order_out, void *workspace,
+                       void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!params || n_members < 1 || n_members >= 0xFFFFFFFFll || !(dt_sec > 0.0) || !order_out || !workspace)
+        return smart_internal_fail(SMART_ERR_BAD_ARG, "smart_member_order: bad argument");
+    const long long padded = pow2_at_least(n_members);
+    char *w = (char *)workspace;
+    OrderState *st = (OrderState *)w;
+    w += align256(sizeof(OrderState));
+    unsigned long long *cand_key = (unsigned long long *)w;
+    w += align256((size_t)padded * 8);
+    unsigned int *cand_row = (unsigned int *)w;
+    const long long slots = smart_member_order_len(n_members);
+    order_init_kernel<<<1, 1, 0, s>>>(st);
+    order_range_kernel<<<grid_for(n_members, 256), 256, 0, s>>>(params, n_members, dt_sec, st);
+    order_keys_kernel<<<grid_for(padded, 256), 256, 0, s>>>(params, n_members, padded, dt_sec, st, cand_key, cand_row);
+    smart_internal_count(3);
+    sort_pairs(cand_key, cand_row, padded, s);
+    order_emit_kernel<<<grid_for(slots, 256), 256, 0, s>>>(cand_row, n_members, slots, st, (long long *)order_out);
+    smart_internal_count(1);
+    SEL_CUDA(cudaGetLastError());
+    return SMART_OK;
+}
+
+int smart_fold_blocks(const double *rows, int64_t n_rows, int32_t n_catchments, int32_t k, double *out,
+                      int32_t *flag_out, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!rows || !out || !flag_out || n_rows < 1 || n_catchments < 1 || k < 1 || n_rows % k != 0)
+        return smart_internal_fail(SMART_ERR_BAD_ARG, "smart_fold_blocks: bad argument (n_rows must be a multiple of k)");
+    const long long n_blocks = n_rows / k;
+    set_flag_kernel<<<1, 1, 0, s>>>(flag_out, 1);
+    fold_blocks_kernel<<<grid_for(n_blocks * n_catchments, 256), 256, 0, s>>>(rows, n_blocks, n_catchments, k, out, flag_out);
+    smart_internal_count(2);
     SEL_CUDA(cudaGetLastError());
     return SMART_OK;
 }

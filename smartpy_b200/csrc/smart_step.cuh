@@ -70,6 +70,16 @@ template <> __device__ __forceinline__ float inv_const<float>(int i)
 __device__ __forceinline__ bool sign_clear(double x) { return __double2hiint(x) >= 0; }
 __device__ __forceinline__ bool sign_clear(float x) { return __float_as_int(x) >= 0; }
 
+// The merged ("fast") form is exact only when no clamp, cap or leak predicate can fire:
+// every routing constant >= dt, inflows >= 0 (0 <= D <= 1, 0 <= H < 1), s' < 1.
+// par = T, C, H, D, S, Z, SK, FK, GK, RK (smartpy/parameters.py:25).
+__device__ __forceinline__ bool fast_form_ok(const double *par, double dt)
+{
+    return par[6] * 3600.0 >= dt && par[7] * 3600.0 >= dt && par[8] * 3600.0 >= dt && par[9] * 3600.0 >= dt &&
+           par[4] >= 0.0 && par[4] <= 0.5 && par[5] > 0.0 && par[3] >= 0.0 && par[3] <= 1.0 && par[2] >= 0.0 &&
+           par[2] <= 0.99 && par[0] > 0.0;
+}
+
 // kGeneral = true : branch-faithful form -- five separate reservoirs with the >= 0 clamps
 //                   (:427-450), the 95 % river cap (:492-498) and the `leak < level`
 //                   predicates (:383, :390, :397).  Needed when dt > k for some store, when
@@ -261,14 +271,27 @@ __device__ __forceinline__ R soil_total(const MemberState<R> &s)
 // Wet hour, soil part (structure.py:360-399): overland split, fill ladder, saturation excess,
 // three leak passes.  ex = rain * T - peva >= 0.  Returns the three merged inflows.
 // hex = (H / Z) * ex, formed by the caller (once per block when the forcing is block-constant).
-template <typename R, int kStride>
+// kTotKnown: the caller guarantees carry.valid (block mode forms the total once per wet block), so
+// the hour starts from carry.tot with no test.  Otherwise the total is re-formed behind a
+// warp-uniform branch: left to predication, the five additions would be issued -- and waited for,
+// the scoreboard does not look at predicates -- in every wet hour of every member.
+// mask: the lanes of the warp that are in this call together (__activemask() taken by the caller
+// where it is known to be stable, e.g. once per wet block).
+template <typename R, int kStride, bool kTotKnown = false>
 __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R> &p, R D, R omD,
-                                              FastCarry<R> &carry, R ex, R hex, R &in_quick, R &in_int, R &in_gw)
+                                              FastCarry<R> &carry, R ex, R hex, unsigned mask, R &in_quick, R &in_int,
+                                              R &in_gw)
 {
     constexpr bool kLeakByDifference = sizeof(R) == 8;
     const R zero = R(0);
     R tot = carry.tot;
-    if (!carry.valid) tot = soil_total(s);
+    if (!kLeakByDifference) {
+        tot = soil_total(s);                        // binary32 state never carries the total
+    } else if (!kTotKnown) {
+        if (__any_sync(mask, !carry.valid)) {
+            if (!carry.valid) tot = soil_total(s);
+        }
+    }
     in_quick = hex * tot;                           // :363-364, h' * excess = (H/Z * excess) * total
     const R u0 = fma(hex, tot, -ex);                // u = -(excess rain still to place) <= 0
     R u = u0;
@@ -283,7 +306,7 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
 #ifndef SMART_NO_EARLY_OUT
     // most often the first layer takes everything for every member of the warp
     const bool done = fill(0);
-    if (__any_sync(__activemask(), !done)) {
+    if (__any_sync(mask, !done)) {
         fill(1); fill(2); fill(3); fill(4); fill(5);
     }
 #else
@@ -389,7 +412,8 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
 
     if (ex_d >= 0.0) {
         const R ex = static_cast<R>(ex_d);
-        fast_wet_soil<R, kStride>(s, p, kc[1 * kStride], kc[2 * kStride], carry, ex, p.Hz * ex, in_quick, in_int, in_gw);
+        fast_wet_soil<R, kStride>(s, p, kc[1 * kStride], kc[2 * kStride], carry, ex, p.Hz * ex, __activemask(), in_quick,
+                                  in_int, in_gw);
     } else {
         fast_dry_soil<R>(s, kc[0], static_cast<R>(-ex_d));
         carry.valid = false;
@@ -403,41 +427,40 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
     s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
 }
 
-// ---- a whole block of `rep` steps under constant forcing (binary64 only) --------------------
+// ---- a whole block of `rep` steps under constant forcing -----------------------------------
 // The reference's own daily -> hourly disaggregation (timeframe.py:167-186) gives every hour of
 // a day the same rain and PET, so the wet/dry predicate holds for the whole block.
 //  * wet block: `rep` hourly steps as above (the soil is nonlinear in its own state);
-//  * dry block: the stores receive nothing for `rep` steps, so they, the river and the two
-//    running sums evolve LINEARLY and are advanced in closed form:
+//  * dry block: the soil ladder over the whole block in closed-form phases (dry_block_soil); the
+//    stores receive nothing for `rep` steps, so they, the river and the two running sums evolve
+//    LINEARLY.  When one block is one reporting step they are advanced in closed form:
 //        V_x(rep) = c_x^rep V_x,    W(rep) = c_w^rep W + sum_x K_x V_x,
 //        K_x = r_x * sum_{h<rep} c_w^(rep-1-h) c_x^h   (Horner sum at set-up, no cancellation),
 //    and what left each store gives the sums by mass balance: sum Q_gw = G - G(rep),
-//    sum Q_out = (W - W(rep)) + sum_x (V_x - V_x(rep)).  Only the soil ladder is walked hour by
-//    hour, or in one subtraction when every member's top layer covers the block's demand.
+//    sum Q_out = (W - W(rep)) + sum_x (V_x - V_x(rep))  (smart_block_fast).  When the run reports
+//    inside the block (report_gap < rep, or 'raw') the stores are walked hour by hour with the
+//    hour's own arithmetic (fast_dry_hour: 7 instructions, no soil, no forcing) and every hour's
+//    outflow is available to the reporting code (run_timeline, block-sub mode).
 // kb[] (binary64 in both precisions, one column per thread): c_sk^rep, c_fk^rep, c_gk^rep,
-// c_rk^rep, K_sk, K_fk, K_gk.  The dry block is evaluated in binary64 also for binary32 state:
-// it costs ~40 instructions per BLOCK, and binary32 powers of (1 - dt/k) would bias the recession.
-// acc += sum of river outflow over the block, agw += sum of groundwater outflow (mm).
+// c_rk^rep, K_sk, K_fk, K_gk.  The closed forms are evaluated in binary64 also for binary32
+// state: ~40 instructions per BLOCK, and binary32 powers of (1 - dt/k) would bias the recession.
 #ifndef SMART_WET_UNROLL
 #define SMART_WET_UNROLL 4
 #endif
 constexpr int kWetUnroll = SMART_WET_UNROLL;   // unroll factor of the wet-block hour loop
 
-// Dry block in closed form (see above): soil per member in phases, stores + river + the two
-// running sums by the linear recurrences.  Always binary64 arithmetic, whatever R is.
-template <typename R, int kStride>
-__device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, const double *kb, double ex_d, int rep,
-                                               R &acc, R &agw)
+// Soil over a whole dry block, per member (a member's arithmetic never depends on the other
+// lanes of its warp).  Nothing refills the layers, so each one runs empty at most once: while
+// layers 0..k-1 are empty the demand reaching layer k is C^k d0 per step (:418).  A layer that is
+// already empty only passes the demand on, decayed by C; otherwise it serves floor(level /
+// demand) whole steps in one multiplication, then one ordinary ladder step (from k down) empties
+// it and the demand decays by C again.  Always binary64 arithmetic, whatever R is.
+template <typename R>
+__device__ __forceinline__ void dry_block_soil(MemberState<R> &s, R Cpar, double ex_d, int rep)
 {
-    // Soil over the whole dry block, per member (a member's arithmetic never depends on the
-    // other lanes of its warp).  Nothing refills the layers, so each one runs empty at most
-    // once: while layers 0..k-1 are empty the demand reaching layer k is C^k d0 per step
-    // (:418).  A layer that is already empty only passes the demand on, decayed by C; otherwise
-    // it serves floor(level / demand) whole steps in one multiplication, then one ordinary
-    // ladder step (from k down) empties it and the demand decays by C again.
     double left = static_cast<double>(rep);      // steps of the block still to account for
     double dem = -ex_d;                          // demand arriving at layer k in each of them
-    const double C = static_cast<double>(kc[0]);
+    const double C = static_cast<double>(Cpar);
     double ly[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) ly[k] = static_cast<double>(s.ly[k]);
@@ -456,8 +479,12 @@ __device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, c
                         left = 0.0;
                         moves_on = false;
                     } else {
-                        // whole steps this layer can serve before it runs empty
-                        const double can = floor(ly[k] / dem);
+                        // whole steps this layer can serve before it runs empty.  The rounded
+                        // quotient can land on the next whole number when the exact one lies just
+                        // below it; the level it would leave is then (slightly) negative: one step
+                        // fewer in that case, so that a layer never goes below zero.
+                        double can = floor(ly[k] / dem);
+                        if (!sign_clear(fma(-can, dem, ly[k]))) can -= 1.0;
                         const double n_full = can < left ? can : left;
                         ly[k] = fma(-n_full, dem, ly[k]);
                         left -= n_full;
@@ -483,6 +510,16 @@ __device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, c
     // (after layer 5 nothing is left to take: remaining steps of the block change nothing)
 #pragma unroll
     for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(ly[k]);
+}
+
+// Dry block with one report at its end: soil as above, stores + river + the two running sums by
+// the linear recurrences.  acc += sum of river outflow over the block, agw += sum of groundwater
+// outflow (mm).
+template <typename R, int kStride>
+__device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, const double *kb, double ex_d, int rep,
+                                               R &acc, R &agw)
+{
+    dry_block_soil<R>(s, kc[0], ex_d, rep);
     const double a = static_cast<double>(s.ove), b = static_cast<double>(s.itf);
     const double g = static_cast<double>(s.sgw), w = static_cast<double>(s.riv);
     const double a_n = a * kb[0 * kStride], b_n = b * kb[1 * kStride], g_n = g * kb[2 * kStride];
@@ -496,6 +533,57 @@ __device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, c
     s.riv = static_cast<R>(w_n);
 }
 
+// Routing constants of a block, fetched once from the per-thread shared-memory column.
+template <typename R>
+struct BlockPar {
+    R D, omD, r_sk, r_fk, r_gk;     // (dt / k of the river stays in shared memory: kc[6], read where it is used)
+};
+template <typename R, int kStride>
+__device__ __forceinline__ BlockPar<R> block_par(const R *kc)
+{
+    BlockPar<R> b;
+    b.D = kc[1 * kStride];
+    b.omD = kc[2 * kStride];
+    b.r_sk = kc[3 * kStride];
+    b.r_fk = kc[4 * kStride];
+    b.r_gk = kc[5 * kStride];
+    return b;
+}
+
+// One wet hour of a block: outflows from the OLD storage (:427-447) -- Q_gw alone (groundwater
+// share) and the river inflow as one fused dot product r_sk V_quick + r_fk V_int + Q_gw (:254) --
+// river, soil, stores.  The caller reads the river store BEFORE the call (its outflow is
+// r_rk * that value).  carry.tot must be valid (kTotKnown).
+template <typename R, int kStride>
+__device__ __forceinline__ void fast_wet_hour(MemberState<R> &s, const FastPar<R> &p, const R *kc, const BlockPar<R> &b,
+                                              FastCarry<R> &carry, R ex, R hex, unsigned mask, R &q_gw, R &q_in)
+{
+    constexpr bool kOneFma = sizeof(R) == 8;
+    q_gw = s.sgw * b.r_gk;
+    q_in = fma(b.r_sk, s.ove, fma(b.r_fk, s.itf, q_gw));
+    s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - s.riv * kc[6 * kStride]) + q_in;
+    R in_quick, in_int, in_gw;
+    fast_wet_soil<R, kStride, sizeof(R) == 8>(s, p, b.D, b.omD, carry, ex, hex, mask, in_quick, in_int, in_gw);
+    s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - s.ove * b.r_sk) + in_quick;
+    s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - s.itf * b.r_fk) + in_int;
+    s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
+}
+
+// One dry hour of a block, routing only (the soil of the whole block is dry_block_soil's): the
+// same arithmetic as the hour above with zero inflows (fma(V, c, 0) == V * c).
+template <typename R, int kStride>
+__device__ __forceinline__ void fast_dry_hour(MemberState<R> &s, const FastPar<R> &p, const R *kc, const BlockPar<R> &b,
+                                              R &q_gw, R &q_in)
+{
+    constexpr bool kOneFma = sizeof(R) == 8;
+    q_gw = s.sgw * b.r_gk;
+    q_in = fma(b.r_sk, s.ove, fma(b.r_fk, s.itf, q_gw));
+    s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - s.riv * kc[6 * kStride]) + q_in;
+    s.ove = kOneFma ? s.ove * p.c_sk : s.ove - s.ove * b.r_sk;
+    s.itf = kOneFma ? s.itf * p.c_fk : s.itf - s.itf * b.r_fk;
+    s.sgw = kOneFma ? s.sgw * p.c_gk : s.sgw - q_gw;
+}
+
 template <typename R, int kStride>
 __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPar<R> &p, const R *kc, const double *kb,
                                                  FastCarry<R> &carry, double ex_d, int rep, R &acc, R &agw)
@@ -503,24 +591,20 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
     constexpr bool kOneFma = sizeof(R) == 8;
     if (ex_d >= 0.0) {
         const R ex = static_cast<R>(ex_d);
-        const R D = kc[1 * kStride], omD = kc[2 * kStride];
+        const BlockPar<R> b = block_par<R, kStride>(kc);
         const R hex = p.Hz * ex;                    // constant over the block
-        const R r_sk = kc[3 * kStride], r_fk = kc[4 * kStride], r_gk = kc[5 * kStride];
+        const unsigned mask = __activemask();       // the lanes walking this wet block together
+        if (kOneFma && !carry.valid) {              // soil total once per block, then carried hour to hour
+            carry.tot = soil_total(s);
+            carry.valid = true;
+        }
         R sum_riv = R(0);                           // river outflow of the block = r_rk * sum of the store
 #pragma unroll kWetUnroll
         for (int h = 0; h < rep; ++h) {
-            // outflows from the OLD storage (:427-447): Q_gw alone (groundwater share), and the river
-            // inflow as one fused dot product r_sk V_quick + r_fk V_int + Q_gw (:254)
-            const R q_gw = s.sgw * r_gk;
-            const R q_in = fma(r_sk, s.ove, fma(r_fk, s.itf, q_gw));
+            R q_gw, q_in;
             sum_riv += s.riv;
+            fast_wet_hour<R, kStride>(s, p, kc, b, carry, ex, hex, mask, q_gw, q_in);
             agw += q_gw;
-            s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - s.riv * kc[6 * kStride]) + q_in;
-            R in_quick, in_int, in_gw;
-            fast_wet_soil<R, kStride>(s, p, D, omD, carry, ex, hex, in_quick, in_int, in_gw);
-            s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - s.ove * r_sk) + in_quick;
-            s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - s.itf * r_fk) + in_int;
-            s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
         }
         acc = kOneFma ? fma(sum_riv, kc[6 * kStride], acc) : acc + sum_riv * kc[6 * kStride];
     } else {

@@ -22,7 +22,6 @@ SCORE_NAMES = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
 FLAG_NO_BLOCK_MODE = 0x10000
 FLAG_NO_REORDER = 0x20000     # engine-level: keep the members in sample order inside the launch
 REORDER_MIN_MEMBERS = 4096    # below this the sort costs more than the divergence it removes
-ORDER_T_BUCKETS = 64.0        # slices of the T range inside which members are ordered by S * Z
 
 
 def _torch():
@@ -71,9 +70,8 @@ class BatchEngine(object):
         self.warm_up_steps = int(warm_up_steps)
         self.extra = extra
         self.gw_constraint = gw_constraint
-        self._order_work = None
-        #: kernels launched by run() so far (bench.py reports the count of its timed region)
-        self.kernel_launches = 0
+        self._order_work = {}     # per stream: (workspace, order slots) of smart_member_order
+        self._staging = {}        # persistent pinned host buffers of run_host(), by name
 
         rain = torch.as_tensor(np.ascontiguousarray(rain, dtype=np.float64) if not torch.is_tensor(rain) else rain)
         peva = torch.as_tensor(np.ascontiguousarray(peva, dtype=np.float64) if not torch.is_tensor(peva) else peva)
@@ -97,11 +95,16 @@ class BatchEngine(object):
         else:
             rows_rain, rows_peva = rain, peva
             n = int(rain.shape[0])
-            if gap > 1 and n % gap == 0 and n >= gap:
-                br = rain.reshape((n // gap, gap) + tuple(rain.shape[1:]))
-                bp = peva.reshape((n // gap, gap) + tuple(peva.shape[1:]))
-                if bool((br == br[:, :1]).all()) and bool((bp == bp[:, :1]).all()):
-                    rows_rain, rows_peva, repeat = br[:, 0].contiguous(), bp[:, 0].contiguous(), gap
+            # candidate block lengths: the reporting step, and one day of simulation steps when the
+            # reporting step divides it (hourly reports of a model forced with daily totals)
+            day = 86400.0 / self.delta_sec
+            candidates = [gap] + ([int(day)] if day == int(day) and int(day) % gap == 0 else [])
+            for k in candidates:
+                if k > 1 and n % k == 0 and n >= k and not (self.flags & FLAG_NO_BLOCK_MODE):
+                    folded = self._fold(rain, k), self._fold(peva, k)
+                    if folded[0] is not None and folded[1] is not None:
+                        rows_rain, rows_peva, repeat = folded[0], folded[1], k
+                        break
         self._rows = (rows_rain, rows_peva)
         self._repeat = repeat
         self._hourly = None if repeat > 1 else (rows_rain, rows_peva)
@@ -146,6 +149,23 @@ class BatchEngine(object):
     def _expand(self, rows, repeat):
         return self._stamp(rows, repeat, 1.0)
 
+    def _fold(self, series, k):
+        """One row per aligned block of k rows if the series is constant inside every block (bit for
+        bit, smart_fold_blocks), else None."""
+        torch = _torch()
+        out = torch.empty((series.shape[0] // k,) + tuple(series.shape[1:]), dtype=torch.float64, device=self.device)
+        flag = torch.empty((1,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.smart_fold_blocks(series.data_ptr(), series.shape[0], self.n_catchments, k, out.data_ptr(),
+                                            flag.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        _native.check(rc)
+        return out if int(flag.item()) == 1 else None
+
+    @property
+    def kernel_launches(self):
+        """Kernels the library has launched so far (its own counter, smart_launch_count)."""
+        return int(self.lib.smart_launch_count())
+
     @property
     def rain(self):
         """Per-step rainfall on the device ([T] or [T, C])."""
@@ -163,8 +183,7 @@ class BatchEngine(object):
     def _block_mode(self, initial_state, last_state):
         """Does this run qualify for one forcing row per reporting step (include/smart_b200.h)?"""
         k = self._repeat
-        return (k > 1 and k == self.report_gap and self.report_type == _native.REPORT_SUMMARY and
-                self.warm_up_steps % k == 0 and initial_state is None and
+        return (k > 1 and k % self.report_gap == 0 and self.warm_up_steps % k == 0 and initial_state is None and
                 not last_state and not (self.flags & FLAG_NO_BLOCK_MODE))
 
     # ------------------------------------------------------------------ descriptor
@@ -204,15 +223,15 @@ class BatchEngine(object):
         dev = self.device
         if scores is None:
             scores = self.obs is not None
-        if scores and self.obs is None:
-            raise Exception("scores requested but the engine has no observations")
         if torch.is_tensor(params):
             p_dev = params.to(dev, torch.float64).contiguous()
         else:
             p_host = np.ascontiguousarray(params, dtype=np.float64)
             if p_host.ndim == 1:
                 p_host = p_host[None, :]
-            pinned = torch.from_numpy(p_host).pin_memory()
+            pinned = self._pinned('run_params', p_host.shape, torch.float64)
+            torch.cuda.current_stream(dev).synchronize()     # the previous copy out of this buffer is done
+            pinned.numpy()[...] = p_host
             p_dev = pinned.to(dev, non_blocking=True)
         if p_dev.dim() != 2 or p_dev.shape[1] != _native.N_PARAMS:
             raise ValueError("params must be [N, 10]")
@@ -235,20 +254,30 @@ class BatchEngine(object):
             d.discharge = q.data_ptr()
             d.ld_discharge = q.stride(0)
             res['discharge'] = q
+        if (scores or best) and self.obs is None:
+            raise Exception("scores / best member requested but the engine has no observations")
         if scores or best:
             d.obs = self.obs.data_ptr()
             d.obs_stats = self.obs_stats.data_ptr()
+        # out['block']: a caller-owned [n, 9] tensor; scores go to its columns 0..7 and gw to column 8
+        # (the row block a sharded run all-gathers), written by the kernel itself
+        blk = out.get('block')
+        if blk is not None and (blk.shape != (n, _native.N_SCORES + 1) or blk.dtype != torch.float64 or
+                                not blk.is_contiguous() or blk.device != dev):
+            raise ValueError("out['block'] must be a contiguous float64 [N, 9] tensor on the engine's device")
         if scores:
-            sc = out.get('scores')
+            sc = blk[:, :_native.N_SCORES] if blk is not None else out.get('scores')
             if sc is None:
                 sc = torch.empty((n, _native.N_SCORES), dtype=torch.float64, device=dev)
             d.scores = sc.data_ptr()
+            d.ld_scores = sc.stride(0) if n > 1 else _native.N_SCORES
             res['scores'] = sc
         if gw:
-            g = out.get('gw')
+            g = blk[:, _native.N_SCORES] if blk is not None else out.get('gw')
             if g is None:
                 g = torch.empty((n,), dtype=torch.float64, device=dev)
             d.gw = g.data_ptr()
+            d.ld_gw = g.stride(0) if n > 1 else 1
             res['gw'] = g
         if last_state:
             ls = torch.empty((n, _native.N_VARS), dtype=torch.float64, device=dev)
@@ -262,101 +291,105 @@ class BatchEngine(object):
                 raise ValueError("initial_state must be [N, 19]")
             d.initial_state = ini.data_ptr()
             keep.append(ini)
-        if best:
-            column, sign = best
-            d.best_column = SCORE_NAMES.index(column) if isinstance(column, str) else int(column)
-            d.best_sign = 1 if sign > 0 else -1
-            ws_bytes = self.lib.smart_batch_workspace_bytes(ctypes.byref(d))
-            ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.float64, device=dev)
-            bs = torch.empty(1, dtype=torch.float64, device=dev)
-            bi = torch.empty(1, dtype=torch.int64, device=dev)
-            d.workspace = ws.data_ptr()
-            d.best_score = bs.data_ptr()
-            d.best_index = bi.data_ptr()
-            keep.append(ws)
-            res['best'] = (bs, bi)
         fn = self.lib.smart_batch_run_f64 if self.precision == 'f64' else self.lib.smart_batch_run_f32
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             if (self.n_catchments == 1 and n >= REORDER_MIN_MEMBERS and not discharge and not last_state
                     and initial_state is None and not (self.flags & FLAG_NO_REORDER)):
-                order = self._order_by_wetness(p_dev, n, stream)
+                order = self._member_order(p_dev, n, stream)
                 d.member_order = order.data_ptr()
-                keep.append(order)
-                self.kernel_launches += self._best_rows_launches(n, n)
+                d.member_order_len = order.numel()
+            if best:
+                column, sign = best
+                d.best_column = SCORE_NAMES.index(column) if isinstance(column, str) else int(column)
+                d.best_sign = 1 if sign > 0 else -1
+                ws_bytes = self.lib.smart_batch_workspace_bytes(ctypes.byref(d))
+                ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.float64, device=dev)
+                bs = torch.empty(1, dtype=torch.float64, device=dev)
+                bi = torch.empty(1, dtype=torch.int64, device=dev)
+                d.workspace = ws.data_ptr()
+                d.best_score = bs.data_ptr()
+                d.best_index = bi.data_ptr()
+                keep.append(ws)
+                res['best'] = (bs, bi)
             rc = fn(ctypes.byref(d), stream.cuda_stream)
         _native.check(rc)
-        # the step kernel is launched in its merged and in its branch-faithful form (each CTA runs in
-        # exactly one of them); last_state takes the single flux-reporting kernel; + the best-member finalize
-        self.kernel_launches += (1 if last_state else (1 if (self.flags & _native.FLAG_FORCE_GENERAL) or
-                                                       initial_state is not None else 2)) + (1 if best else 0)
         for t in keep:   # keep inputs alive until the stream has consumed them
             t.record_stream(stream)
         return res
 
-    @staticmethod
-    def _best_rows_launches(n, k):
-        """Kernel launches of one smart_best_rows(n, k) call (mirrors the loop in smart_select.cu)."""
-        padded = 1
-        while padded < k:
-            padded <<= 1
-        chunk = min(padded, 2048)
-        launches = 2 + 24 + 1 + (1 if padded > k else 0) + 1      # init, keys, 12 x (histogram, pick), gather, pad, emit
-        if padded > 1:
-            launches += 1
-            kk = 2 * chunk
-            while kk <= padded:
-                j = kk >> 1
-                while j >= chunk:
-                    launches += 1
-                    j >>= 1
-                launches += 1
-                kk <<= 1
-        return launches
-
-    def _order_by_wetness(self, p_dev, n, stream):
-        """Member indices grouped so that the lanes of a warp take the same branches, sorted on the
-        device with the library's own radix select + sort (smart_best_rows with k = n).
-
-        The key is member_order_key().  Results do not change by a bit: a member's arithmetic never
-        depends on its neighbours."""
+    def _member_order(self, p_dev, n, stream):
+        """Slots of the launch (smart_member_order): members grouped so that the lanes of a warp take
+        the same branches -- inside the fast form's domain first (padded to a CTA boundary), the
+        others after; each group by slice of T, then by S * Z.  Results do not change by a bit: a
+        member's arithmetic never depends on its neighbours.  Workspace and slots are kept per
+        stream (two runs on one stream are ordered; runs on different streams do not share them)."""
         torch = _torch()
-        order = torch.empty((n,), dtype=torch.int64, device=self.device)
-        nbytes = self.lib.smart_condition_workspace_bytes(n, n)
-        work = self._order_work
-        if work is None or work.numel() < nbytes:
-            work = self._order_work = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
-        key = member_order_key(p_dev)
-        key.record_stream(stream)
-        _native.check(self.lib.smart_best_rows(key.data_ptr(), n, 1, 0, None, 0, n,
-                                               order.data_ptr(), None, work.data_ptr(), stream.cuda_stream))
+        slots = int(self.lib.smart_member_order_len(n))
+        nbytes = int(self.lib.smart_member_order_workspace_bytes(n))
+        work, order = self._order_work.get(stream.cuda_stream, (None, None))
+        if work is None or work.numel() < nbytes or order.numel() != slots:
+            work = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+            order = torch.empty((slots,), dtype=torch.int64, device=self.device)
+            self._order_work[stream.cuda_stream] = (work, order)
+        _native.check(self.lib.smart_member_order(p_dev.data_ptr(), n, self.delta_sec, order.data_ptr(),
+                                                  work.data_ptr(), stream.cuda_stream))
         return order
+
+    # ------------------------------------------------------------------ host buffers in, host buffers out
+    def _pinned(self, name, shape, dtype):
+        torch = _torch()
+        buf = self._staging.get(name)
+        if buf is None or buf.shape != tuple(shape) or buf.dtype != dtype:
+            buf = self._staging[name] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
+        return buf
+
+    def run_host(self, params, discharge=False, gw=True):
+        """params: numpy [N, 10] on the host -> dict of numpy arrays on the host ('scores' [N, 8] when
+        the engine has observations, 'gw' [N], 'discharge' [n_report, N] on request).  The copies go
+        through pinned staging buffers the engine keeps from call to call (no pin_memory() or
+        allocation on the steady path) and the call returns when the results are in host memory."""
+        torch = _torch()
+        dev = self.device
+        p_host = np.ascontiguousarray(params, dtype=np.float64)
+        if p_host.ndim == 1:
+            p_host = p_host[None, :]
+        n = p_host.shape[0]
+        scored = self.obs is not None
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev)
+            p_pin = self._pinned('params', p_host.shape, torch.float64)
+            p_pin.numpy()[...] = p_host
+            p_dev = self._device_buffer('params', p_host.shape)
+            p_dev.copy_(p_pin, non_blocking=True)
+            blk = self._device_buffer('block', (n, _native.N_SCORES + 1))
+            res = self.run(p_dev, discharge=discharge, scores=scored, gw=True, out={'block': blk})
+            blk_pin = self._pinned('block', blk.shape, torch.float64)
+            blk_pin.copy_(blk, non_blocking=True)
+            out = {}
+            if discharge:
+                q_pin = self._pinned('discharge', res['discharge'].shape, res['discharge'].dtype)
+                q_pin.copy_(res['discharge'], non_blocking=True)
+            stream.synchronize()
+        table = blk_pin.numpy()
+        if scored:
+            out['scores'] = table[:, :_native.N_SCORES]
+        if gw:
+            out['gw'] = table[:, _native.N_SCORES]
+        if discharge:
+            out['discharge'] = q_pin.numpy()
+        return out
+
+    def _device_buffer(self, name, shape):
+        torch = _torch()
+        buf = self._staging.get('dev_' + name)
+        if buf is None or buf.shape != tuple(shape):
+            buf = self._staging['dev_' + name] = torch.empty(tuple(shape), dtype=torch.float64, device=self.device)
+        return buf
 
     # steps one launch of n members walks through (warm-up + main), for throughput accounting
     def member_steps(self, n_members):
         return int(n_members) * (self.n_steps + self.warm_up_steps)
-
-
-def member_order_key(params):
-    """Sort key [N] (float64, same device as params[N, 10]) that groups the members of a launch
-    so that the lanes of a warp take the same branches.
-
-    Integer part: slice of T (ORDER_T_BUCKETS equal slices of the sample's range).  Whether a
-    step is wet depends on the member through `rain * T - peva >= 0` only: with neighbouring T a
-    warp no longer walks a wet block for the sake of a few lanes (3-4 % of the wet-block work of
-    an LHS sample in sample order).  Fraction: S * Z scaled into [0, 1): the room the leaks open
-    in the top soil layer every hour grows with S and with the water the column holds (~ Z), and
-    that room decides whether the fill ladder stops after the first layer for the whole warp.
-    (Traces of 1,536 members with the CPU oracle: instructions above the no-divergence floor inside
-    one slice of T: +6.2 % in sample order, +4.2 % ordered by S, +4.7 % by Z, +1.5 % by S * Z,
-    +1.4 % with the members ordered by their true rate of deep fills.)"""
-    torch = _torch()
-    t = params[:, 0]
-    x = params[:, 4] * params[:, 5]
-    tmin, tmax = torch.aminmax(t)
-    xmin, xmax = torch.aminmax(x)
-    slices = torch.clamp(torch.floor((t - tmin) / (tmax - tmin + 1e-300) * ORDER_T_BUCKETS), max=ORDER_T_BUCKETS - 1)
-    return (slices + (x - xmin) / (xmax - xmin + 1e-300) * 0.999).contiguous()
 
 
 def warm_up_length(warm_up_days, delta_sec):

@@ -24,7 +24,7 @@ def client(tmp_path_factory):
 
 def test_c_client_links_and_validates(client):
     out = subprocess.check_output([client], text=True)
-    assert "smart_version 100" in out and "empty descriptor -> -1" in out
+    assert "smart_version 200" in out and "empty descriptor -> -1" in out
 
 
 @pytest.mark.gpu

@@ -1,0 +1,328 @@
+"""GPU parity tests added in round 2 (all through the C ABI):
+
+  * the reference's own `smartcpp` call sequence replayed through the GPU shim
+    (smartpy/structure.py:100-121, :143-146: initial guess -> warm-up allsteps (8760, 1, 24) taking
+    [2] -> main allsteps (87672, 1, 24)) against the reference-generated golden;
+  * FP32 state against the FP64 kernel over the WHOLE C2 batch (1e5 LHS members) and over a 1e4
+    subsample at the C3 length (30 years): max |dNSE|, |dKGE| < 1e-5 (BASELINE.json north_star),
+    distributions written to gpurun_out/ (kept under profiles/);
+  * block-sub mode (forcing constant inside a day, reports inside it: hourly output of a model
+    forced with daily totals -- BASELINE config 4a -- and 'raw' reporting) against the oracle,
+    single and multi catchment, including C4a at full size (1e4 catchments x 100 members x 8,760
+    hourly steps, hourly discharge written, 32 members spot-checked);
+  * member grouping by the library (smart_member_order): slot layout against a numpy restatement,
+    members outside the fast form's domain in CTAs of their own, no bit changed;
+  * scores + gw written by the kernel into a caller-given [N, 9] block; the host-buffer API.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden, EXTRA
+from test_gpu_parity import make_engine, relmax, RTOL_Q, ATOL_F32
+
+pytestmark = pytest.mark.gpu
+
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _record(name, payload):
+    """Keep a measured distribution next to the other GPU-side artefacts (copied to profiles/)."""
+    try:
+        os.makedirs(OUT, exist_ok=True)
+        with open(os.path.join(OUT, name), "w") as f:
+            json.dump(payload, f, indent=1)
+    except OSError:
+        pass
+
+
+def _quantiles(x):
+    x = np.asarray(x, dtype=np.float64)
+    return {"max": float(x.max()), "p999": float(np.quantile(x, 0.999)), "p99": float(np.quantile(x, 0.99)),
+            "p50": float(np.quantile(x, 0.5)), "mean": float(x.mean()), "n": int(x.size),
+            "over_1e-5": int((x >= 1e-5).sum())}
+
+
+# ---------------------------------------------------------------- the reference's hook sequence on the GPU
+def test_reference_hook_call_sequence_through_gpu_shim(catchment):
+    """What the unmodified reference does when `import smartcpp` succeeds (structure.py:56-62):
+    nd_initial_wu from the `extra` guess (:100-116), nd_initial = allsteps(..., 8760, ..., 1, 24)[2]
+    (:118-121), then allsteps(..., 87672, ..., nd_initial, 1, 24)[0:2] (:143-146).  Same calls, same
+    arguments (the FULL forcing arrays are passed to the warm-up call), through smartcpp_shim on
+    the GPU; the result must be the reference's own discharge (tests/golden/runs_single.npz)."""
+    from smartpy_b200 import smartcpp_shim
+    g = load_golden("runs_single")
+    p = g["p_test"]
+    area, dt = catchment.area, 3600.0
+    SK, FK, GK, RK, Z = p[6], p[7], p[8], p[9], p[5]
+    ini = np.zeros(19)
+    ini[7:12] = [EXTRA['aar'] * EXTRA['r-o_ratio'] * EXTRA['r-o_split'][j] / 1000 * area / 8766 * k
+                 for j, k in enumerate((SK, SK, FK, GK, GK))]
+    ini[18] = EXTRA['aar'] * EXTRA['r-o_ratio'] / 1000 * area / 8766 * RK
+    ini[12:18] = (Z / 12) / 1000 * area
+    warm = smartcpp_shim.allsteps(area, dt, 8760, catchment.rain, catchment.peva, p, ini, 1, 24)
+    assert isinstance(warm, tuple) and warm[0].shape == (365,) and warm[2].shape == (19,)
+    nd_initial = np.zeros(19)
+    nd_initial[:] = warm[2]                                   # structure.py:118 assigns [2] into the row
+    out = smartcpp_shim.allsteps(area, dt, 87672, catchment.rain, catchment.peva, p, nd_initial, 1, 24)[0:2]
+    assert out[0].shape == (3653,)
+    assert relmax(out[0], g["q_summary"]) < RTOL_Q
+    assert abs(out[1] - float(g["gw_summary"])) < 1e-10 * float(g["gw_summary"])
+    # 'raw' reporting through the same hook (report_type 2)
+    raw = smartcpp_shim.allsteps(area, dt, 87672, catchment.rain, catchment.peva, p, nd_initial, 2, 24)
+    assert relmax(raw[0], g["q_raw"]) < RTOL_Q
+
+
+# ---------------------------------------------------------------- FP32 state against FP64, whole batches
+def test_fp32_against_fp64_over_the_whole_c2_batch(catchment):
+    import bench
+    params = bench.lhs_rows(100000, 42)
+    a = make_engine(catchment, precision='f64').run(params, discharge=False, scores=True, gw=True)
+    b = make_engine(catchment, precision='f32').run(params, discharge=False, scores=True, gw=True)
+    s64, s32 = a["scores"].cpu().numpy(), b["scores"].cpu().numpy()
+    assert np.isfinite(s64[:, :7]).all() and np.isfinite(s32[:, :7]).all()
+    d_nse, d_kge = np.abs(s32[:, 0] - s64[:, 0]), np.abs(s32[:, 1] - s64[:, 1])
+    d_gw = np.abs(b["gw"].cpu().numpy() - a["gw"].cpu().numpy())
+    _record("fp32_vs_fp64_c2.json", {"config": "C2: LHS 1e5 (seed 42) x test catchment, 87,672 + 8,760 steps",
+                                     "abs_dNSE": _quantiles(d_nse), "abs_dKGE": _quantiles(d_kge),
+                                     "abs_dGW": _quantiles(d_gw), "bar": ATOL_F32,
+                                     "worst_nse_member": params[int(d_nse.argmax())].tolist()})
+    assert d_nse.max() < ATOL_F32, d_nse.max()
+    assert d_kge.max() < ATOL_F32, d_kge.max()
+
+
+def test_fp32_against_fp64_at_c3_length(oracle_lib):
+    """1e4-member subsample of C3 (30 years hourly, 262,992 + 8,760 steps): FP32 state against the
+    FP64 kernel on all of them and against the oracle on 32."""
+    import bench
+    from smartpy_b200.engine import BatchEngine
+    from oracle import scores as oscores
+    w = bench.make_workload("c3", 0, members=10000)
+    kw = dict(obs=w["obs"], extra=w["extra"], warm_up_steps=w["warm_steps"], gw_constraint=w["gwc"])
+    a = BatchEngine(w["rain"], w["peva"], w["area"], w["dt"], w["gap"], precision='f64', **kw).run(w["params"])
+    b = BatchEngine(w["rain"], w["peva"], w["area"], w["dt"], w["gap"], precision='f32', **kw).run(w["params"])
+    s64, s32 = a["scores"].cpu().numpy(), b["scores"].cpu().numpy()
+    d_nse, d_kge = np.abs(s32[:, 0] - s64[:, 0]), np.abs(s32[:, 1] - s64[:, 1])
+    pick = np.linspace(0, 9999, 32).astype(int)
+    q_ref, gw_ref = oracle_lib.run_members(w["area"], w["dt"], w["rain"], w["peva"], w["params"][pick], w["extra"],
+                                           w["n_steps"], w["gap"], warm_up=365)
+    sc_ref = oscores.score_members(q_ref, gw_ref, w["obs"], w["gwc"])
+    o_nse, o_kge = np.abs(s32[pick, 0] - sc_ref[:, 0]), np.abs(s32[pick, 1] - sc_ref[:, 1])
+    _record("fp32_vs_fp64_c3.json", {"config": "C3 length: LHS 1e4 (seed 42) x 30 yr synthetic forcing, 262,992 + 8,760 steps",
+                                     "abs_dNSE": _quantiles(d_nse), "abs_dKGE": _quantiles(d_kge),
+                                     "vs_oracle_32": {"abs_dNSE_max": float(o_nse.max()), "abs_dKGE_max": float(o_kge.max())},
+                                     "bar": ATOL_F32})
+    assert np.max(np.abs(s64[pick, :7] - sc_ref[:, :7]) / np.maximum(1.0, np.abs(sc_ref[:, :7]))) < 1e-10
+    assert d_nse.max() < ATOL_F32 and d_kge.max() < ATOL_F32, (d_nse.max(), d_kge.max())
+    assert o_nse.max() < ATOL_F32 and o_kge.max() < ATOL_F32, (o_nse.max(), o_kge.max())
+
+
+# ---------------------------------------------------------------- block-sub mode: reports inside a day
+@pytest.mark.parametrize("gap,report,precision", [(1, "raw", "f64"), (1, "summary", "f64"), (6, "summary", "f64"),
+                                                   (8, "raw", "f64"), (24, "raw", "f64"), (12, "summary", "f32")])
+def test_block_sub_mode_matches_oracle(catchment, oracle_lib, gap, report, precision):
+    from smartpy_b200.engine import BatchEngine, warm_up_length, FLAG_NO_BLOCK_MODE
+    g = load_golden("runs_members")
+    days = 400
+    n = days * 24
+    daily_rain = catchment.rain[:n:24] * 24.0
+    daily_peva = catchment.peva[:n:24] * 24.0
+    obs = None
+    kw = dict(extra=EXTRA, warm_up_steps=warm_up_length(30, 3600.0), report=report, precision=precision)
+    eng = BatchEngine(daily_rain, daily_peva, catchment.area, 3600.0, gap, obs=obs, forcing_repeat=24, **kw)
+    assert eng._block_mode(None, False)
+    res = eng.run(g["params"], discharge=True, scores=False, gw=True)
+    q = res["discharge"].cpu().numpy().T.astype(np.float64)
+    assert q.shape == (len(g["params"]), n // gap)
+    # the same run through the per-step path (one forcing row per step): every path agrees with the oracle
+    per_step = BatchEngine(catchment.rain[:n], catchment.peva[:n], catchment.area, 3600.0, gap, obs=obs,
+                           flags=FLAG_NO_BLOCK_MODE, **kw)
+    assert not per_step._block_mode(None, False)
+    q_step = per_step.run(g["params"], discharge=True, scores=False)["discharge"].cpu().numpy().T.astype(np.float64)
+    tol = RTOL_Q if precision == "f64" else 2e-3
+    for m in (0, 7, 19, 33, 39):
+        q_ref, gw_ref = oracle_lib.run(catchment.area, 3600.0, catchment.rain[:n], catchment.peva[:n], g["params"][m],
+                                       EXTRA, n, gap, report=report, warm_up=30)
+        assert relmax(q[m], q_ref) < tol
+        assert relmax(q_step[m], q_ref) < tol
+        assert abs(float(res["gw"][m]) - gw_ref) < (1e-9 if precision == "f64" else 1e-4) * gw_ref
+
+
+def test_block_constant_hourly_series_is_detected_for_hourly_reports(catchment):
+    """A per-step series that is constant inside days (what timeframe.py:167-186 produces) with
+    HOURLY reporting: the engine folds it to one row per day (smart_fold_blocks) and the run takes
+    block-sub mode; a series that is not block-constant stays on the per-step path."""
+    import torch
+    from smartpy_b200.engine import BatchEngine
+    n = 24 * 50
+    eng = BatchEngine(catchment.rain[:n], catchment.peva[:n], catchment.area, 3600.0, 1, extra=EXTRA, report='raw')
+    assert eng._repeat == 24 and eng._rows[0].shape == (50,)
+    assert torch.equal(eng.rain, torch.from_numpy(catchment.rain[:n]).to(eng.rain.device))
+    rain = catchment.rain[:n].copy()
+    rain[100] *= 1.0000001
+    eng2 = BatchEngine(rain, catchment.peva[:n], catchment.area, 3600.0, 1, extra=EXTRA, report='raw')
+    assert eng2._repeat == 1 and not eng2._block_mode(None, False)
+
+
+def test_c4a_full_size_against_oracle(oracle_lib):
+    """BASELINE config 4a: 1e4 synthetic catchments x 100 members, [t][catchment] daily forcing
+    split on the device, 8,760 hourly steps, gap 1, hourly discharge written ([8760][1e6] f64 =
+    70 GB); 32 members spot-checked against the oracle."""
+    import torch
+    import bench
+    from smartpy_b200.engine import BatchEngine
+    w = bench.make_workload("c4a", 0)
+    n = w["n_members"]
+    assert n == 1000000 and w["n_steps"] == 8760 and w["gap"] == 1
+    eng = BatchEngine(w["rain"], w["peva"], w["area"], w["dt"], w["gap"], obs=None, extra=w["extra"],
+                      warm_up_steps=w["warm_steps"], report=w["report"], members_per_catchment=w["mpc"],
+                      forcing_repeat=w.get("forcing_repeat", 1))
+    assert eng._block_mode(None, False)
+    res = eng.run(w["params"], discharge=True, scores=False, gw=True)
+    q = res["discharge"]
+    assert q.shape == (8760, n)
+    rng = np.random.RandomState(3)
+    pick = np.concatenate([[0, 99, 100, n - 1], rng.choice(n, 28, replace=False)])
+    k = w.get("forcing_repeat", 1)
+    for m in pick:
+        c = int(m) // w["mpc"]
+        rain = np.repeat(w["rain"][:, c] / k, k) if k > 1 else w["rain"][:, c].copy()
+        peva = np.repeat(w["peva"][:, c] / k, k) if k > 1 else w["peva"][:, c].copy()
+        q_ref, gw_ref = oracle_lib.run(float(w["area"][c]), w["dt"], rain, peva, w["params"][m], w["extra"], 8760, 1,
+                                       report='raw')
+        assert relmax(q[:, int(m)].cpu().numpy(), q_ref) < RTOL_Q
+        assert abs(float(res["gw"][int(m)]) - gw_ref) < 1e-9 * gw_ref
+    assert bool(torch.isfinite(q[::97]).all())
+
+
+# ---------------------------------------------------------------- member grouping by the library
+def _fast_ok(p, dt=3600.0):
+    T, C, H, D, S, Z, SK, FK, GK, RK = p
+    return bool(min(SK, FK, GK, RK) * 3600.0 >= dt and 0.0 <= S <= 0.5 and Z > 0.0 and 0.0 <= D <= 1.0
+                and 0.0 <= H <= 0.99 and T > 0.0)
+
+
+WILD = np.array([
+    [1.0, 0.5, 0.2, 0.3, 1.5, 60.0, 0.5, 2.0, 30.0, 0.2],
+    [1.05, 0.9, 0.6, 0.5, 3.0, 20.0, 5.0, 10.0, 12.0, 3.0],
+    [0.95, 0.1, 0.1, 0.9, 0.9, 100.0, 30.0, 30.0, 30.0, 30.0],
+    [1.0, 0.5, 0.995, 1.0, 0.01, 50.0, 1.0, 48.0, 1200.0, 1.0],
+])
+
+
+def test_member_order_slots_match_numpy_restatement():
+    import torch
+    import bench
+    from smartpy_b200 import _native
+    lib = _native.load()
+    n = 20000 + 77
+    params = bench.lhs_rows(n, 3)
+    rng = np.random.RandomState(4)
+    wild_at = rng.choice(n, 300, replace=False)
+    params[wild_at] = WILD[rng.randint(0, len(WILD), 300)] * rng.uniform(0.99, 1.01, (300, 1))
+    dev = torch.device("cuda")
+    p_dev = torch.from_numpy(params).to(dev)
+    slots = lib.smart_member_order_len(n)
+    order = torch.empty((slots,), dtype=torch.int64, device=dev)
+    work = torch.empty((lib.smart_member_order_workspace_bytes(n),), dtype=torch.uint8, device=dev)
+    _native.check(lib.smart_member_order(p_dev.data_ptr(), n, 3600.0, order.data_ptr(), work.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+    got = order.cpu().numpy()
+    # numpy restatement of csrc/smart_select.cu: key = group * 128 + slice of T + S * Z scaled into [0, 0.999]
+    T, X = params[:, 0], params[:, 4] * params[:, 5]
+    slices = np.minimum(np.floor((T - T.min()) / (T.max() - T.min() + 1e-300) * 64.0), 63.0)
+    frac = (X - X.min()) / (X.max() - X.min() + 1e-300) * 0.999
+    fast = np.array([_fast_ok(p) for p in params])
+    key = np.where(fast, 0.0, 128.0) + slices + frac
+    expect_sorted = np.lexsort((np.arange(n), key))                # ties by row, as the (key, row) pair sort does
+    n_fast = int(fast.sum())
+    general_at = -(-n_fast // 128) * 128
+    expect = np.full(slots, -1, dtype=np.int64)
+    expect[:n_fast] = expect_sorted[:n_fast]
+    expect[general_at:general_at + (n - n_fast)] = expect_sorted[n_fast:]
+    assert np.array_equal(got, expect)
+    assert sorted(got[got >= 0].tolist()) == list(range(n))
+
+
+def test_wild_members_run_in_their_own_ctas_and_change_no_bit(catchment, oracle_lib):
+    """1 % of a batch outside the fast form's domain: the grouping puts them in CTAs of their own
+    (general kernel, launched beside the fast one), every other member keeps the bits it has in a
+    batch without them, and the wild members agree with the oracle."""
+    import bench
+    from smartpy_b200.engine import REORDER_MIN_MEMBERS
+    n = 4 * REORDER_MIN_MEMBERS + 5
+    n_steps = 24 * 400
+    tame = bench.lhs_rows(n, 11)
+    rng = np.random.RandomState(12)
+    wild_at = np.sort(rng.choice(n, n // 100, replace=False))
+    mixed = tame.copy()
+    mixed[wild_at] = WILD[rng.randint(0, len(WILD), len(wild_at))]
+    eng = make_engine(catchment, n_steps=n_steps)
+    a = eng.run(tame, discharge=False, scores=True, gw=True)
+    b = eng.run(mixed, discharge=False, scores=True, gw=True)
+    sa, sb = a["scores"].cpu().numpy(), b["scores"].cpu().numpy()
+    keep = np.ones(n, dtype=bool)
+    keep[wild_at] = False
+    assert np.array_equal(sa[keep], sb[keep], equal_nan=True)
+    assert np.array_equal(a["gw"].cpu().numpy()[keep], b["gw"].cpu().numpy()[keep])
+    from oracle import scores as oscores
+    pick = wild_at[:6]
+    q_ref, gw_ref = oracle_lib.run_members(catchment.area, 3600.0, catchment.rain[:n_steps], catchment.peva[:n_steps],
+                                           mixed[pick], EXTRA, n_steps, 24, warm_up=365)
+    sc_ref = oscores.score_members(q_ref, gw_ref, catchment.obs[:n_steps // 24], 0.12667)
+    assert np.max(np.abs(sb[pick, :7] - sc_ref[:, :7]) / np.maximum(1.0, np.abs(sc_ref[:, :7]))) < 1e-9
+
+
+# ---------------------------------------------------------------- [N, 9] block output, host-buffer API
+def test_scores_and_gw_written_into_a_gather_block(catchment):
+    import torch
+    g = load_golden("runs_members")
+    eng = make_engine(catchment, n_steps=24 * 300)
+    ref = eng.run(g["params"], scores=True, gw=True)
+    blk = torch.full((len(g["params"]), 9), -7.0, dtype=torch.float64, device=ref["gw"].device)
+    res = eng.run(g["params"], scores=True, gw=True, out={"block": blk})
+    assert res["scores"].data_ptr() == blk.data_ptr()
+    assert torch.equal(blk[:, :7], ref["scores"][:, :7]) and torch.equal(blk[:, 8], ref["gw"])
+    assert torch.equal(torch.isnan(blk[:, 7]), torch.isnan(ref["scores"][:, 7]))
+    with pytest.raises(ValueError):
+        eng.run(g["params"], scores=True, out={"block": blk[:, :8]})
+
+
+def test_run_host_round_trip_reuses_its_staging(catchment):
+    g = load_golden("runs_members")
+    eng = make_engine(catchment, n_steps=24 * 300)
+    dev = eng.run(g["params"], scores=True, gw=True)
+    out = eng.run_host(g["params"])
+    assert isinstance(out["scores"], np.ndarray) and out["scores"].shape == (len(g["params"]), 8)
+    assert np.array_equal(out["scores"], dev["scores"].cpu().numpy(), equal_nan=True)
+    assert np.array_equal(out["gw"], dev["gw"].cpu().numpy())
+    staging = {k: v.data_ptr() for k, v in eng._staging.items()}
+    again = eng.run_host(g["params"][::-1].copy())
+    assert {k: v.data_ptr() for k, v in eng._staging.items()} == staging     # no new pinned or device buffers
+    assert np.array_equal(again["scores"][::-1], out["scores"], equal_nan=True)
+    # the C entry point with host pointers: a second call of the same size allocates nothing new
+    import ctypes
+    from smartpy_b200 import _native
+    lib = _native.load()
+    n, days = 5, 100
+    params = np.ascontiguousarray(g["params"][:n])
+    rain = np.ascontiguousarray(catchment.rain[:days * 24])
+    peva = np.ascontiguousarray(catchment.peva[:days * 24])
+    area = np.array([catchment.area])
+    obs = np.ascontiguousarray(catchment.obs[:days])
+    table = np.zeros((n, 9))
+    d = _native.BatchDesc()
+    d.n_members, d.n_steps, d.n_warmup, d.n_catchments, d.members_per_catchment = n, days * 24, 0, 1, 1
+    d.report_gap, d.report_type, d.dt_sec = 24, 1, 3600.0
+    d.params, d.rain, d.peva, d.area_m2, d.obs = (params.ctypes.data, rain.ctypes.data, peva.ctypes.data,
+                                                  area.ctypes.data, obs.ctypes.data)
+    d.gw_constraint = float('nan')
+    d.scores, d.ld_scores, d.gw, d.ld_gw = table.ctypes.data, 9, table.ctypes.data + 64, 9
+    _native.check(lib.smart_batch_run_host(ctypes.byref(d), 64, 0))
+    first = table.copy()
+    table[:] = 0
+    _native.check(lib.smart_batch_run_host(ctypes.byref(d), 64, 0))
+    assert np.array_equal(first, table, equal_nan=True) and np.isfinite(table[:, :7]).all() and (table[:, 8] > 0).all()
+    assert lib.smart_host_arena_release() == 0

@@ -261,31 +261,28 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_native.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.smart_version() == 100
+    assert lib.smart_version() == 200
     # argument validation happens before any CUDA call, so it is testable without a GPU
     d = _native.BatchDesc()
     assert lib.smart_batch_run_f64(ctypes.byref(d), None) == _native.ERR_BAD_ARG
     assert "n_members" in _native.last_error()
 
 
-def test_member_order_key_groups_by_t_slice_then_s_times_z():
-    """engine.member_order_key on a CPU tensor (the sort itself is the library's, GPU-tested):
-    sorting by the key = numpy lexsort on (slice of T, S * Z); degenerate samples do not divide by 0."""
-    import torch
-    from smartpy_b200.engine import member_order_key, ORDER_T_BUCKETS
-    from smartpy_b200.montecarlo.lhs import latin_hypercube
-    from smartpy_b200.parameters import Parameters
-    p = Parameters()
-    params = latin_hypercube(5000, [p.ranges[n] for n in p.names], rng=np.random.RandomState(2))
-    key = member_order_key(torch.from_numpy(params))
-    assert key.shape == (5000,) and key.dtype == torch.float64 and key.is_contiguous()
-    key = key.numpy()
-    T, SZ = params[:, 0], params[:, 4] * params[:, 5]
-    slices = np.minimum(np.floor((T - T.min()) / (T.max() - T.min() + 1e-300) * ORDER_T_BUCKETS), ORDER_T_BUCKETS - 1)
-    assert np.array_equal(np.floor(key), slices) and slices.max() == ORDER_T_BUCKETS - 1
-    assert np.array_equal(np.argsort(key, kind='stable'), np.lexsort((SZ, slices)))
-    same = np.tile(params[:1], (10, 1))
-    assert np.array_equal(member_order_key(torch.from_numpy(same)).numpy(), np.zeros(10))
+def test_member_order_sizes_are_host_functions():
+    """smart_member_order_len / _workspace_bytes need no device: the fast group padded to a CTA
+    boundary (128) plus the other group always fit; the workspace holds the sort's padded pairs."""
+    from smartpy_b200 import _native, _build
+    _build.build()
+    lib = _native.load()
+    for n in (1, 127, 128, 129, 100000, 1250000):
+        slots = lib.smart_member_order_len(n)
+        assert slots % 128 == 0 and slots >= n + 127 and slots <= n + 255
+        padded = 1 << max(n - 1, 0).bit_length()
+        assert lib.smart_member_order_workspace_bytes(n) >= padded * 12
+    # argument validation before any CUDA call
+    assert lib.smart_member_order(None, 5, 3600.0, None, None, None) == _native.ERR_BAD_ARG
+    assert lib.smart_fold_blocks(None, 48, 1, 24, None, None, None) == _native.ERR_BAD_ARG
+    assert lib.smart_launch_count() >= 0
 
 
 def test_binary64_unit_is_built_without_implicit_contraction():

@@ -43,3 +43,33 @@ def test_step_formulations_match_reference_goldens(emulator, catchment, mode, la
         worst_gw = max(worst_gw, abs(gw.value - g["gw"][i]) / g["gw"][i])
     assert worst_q < bound, (label, worst_q)        # far inside the 1e-10 bar of BASELINE.json
     assert worst_gw < 1e-11
+
+
+@pytest.mark.parametrize("gap,report,n_days", [(24, "raw", 3653), (1, "raw", 500), (1, "summary", 300), (6, "summary", 500),
+                                                (8, "raw", 500)])
+def test_block_sub_mode_matches_oracle(emulator, catchment, oracle_lib, gap, report, n_days):
+    """Blocks of 24 constant-forcing steps with reports INSIDE the block (kModeBlockSub of
+    run_timeline: hourly output of a model forced with daily totals, or 'raw' reporting), against
+    the oracle's hour-by-hour run (structure.py:181-195 handles every gap with one loop)."""
+    dp = ctypes.POINTER(ctypes.c_double)
+    emulator.emulate_run_sub.argtypes = [ctypes.c_int] + emulator.emulate_run.argtypes[1:]
+    g = load_golden("runs_members")
+    split = np.array([0.10, 0.15, 0.15, 0.30, 0.30])
+    n = 24 * n_days
+    rain, peva = np.ascontiguousarray(catchment.rain[:n]), np.ascontiguousarray(catchment.peva[:n])
+    rtype = 1 if report == "summary" else 2
+    worst_q = worst_gw = 0.0
+    for i in (0, 3, 11, 17, 25, 33, 39):
+        p = np.ascontiguousarray(g["params"][i])
+        q = np.zeros(n // gap)
+        gw = ctypes.c_double()
+        emulator.emulate_run_sub(24, catchment.area, 3600.0, n, 24 * 30, rain.ctypes.data_as(dp), peva.ctypes.data_as(dp),
+                                 p.ctypes.data_as(dp), 1, 1200 * 0.45, split.ctypes.data_as(dp), rtype, gap,
+                                 q.ctypes.data_as(dp), ctypes.byref(gw))
+        q_ref, gw_ref = oracle_lib.run(catchment.area, 3600.0, rain, peva, p, catchment.extra, n, gap, report=report,
+                                       warm_up=30)
+        assert q_ref.shape == q.shape
+        worst_q = max(worst_q, float(np.max(np.abs(q - q_ref) / q_ref)))
+        worst_gw = max(worst_gw, abs(gw.value - gw_ref) / gw_ref)
+    assert worst_q < 1e-11, worst_q
+    assert worst_gw < 1e-11, worst_gw

@@ -19,11 +19,12 @@ static inline int __any_sync(unsigned, int p) { return p; }
 
 using namespace smart;
 
-// mode 0: general, 1: fast (first form), 2: fast V2.  Mirrors run_member/run_timeline of
-// smart_kernels.cu for one member, summary or raw reporting.
-extern "C" int emulate_run(int mode, double area, double dt, long T, long W, const double *rain,
-                           const double *peva, const double *par, int has_extra, double aar_ro,
-                           const double *split, int report_type, int gap, double *discharge, double *gw_out)
+// mode 0: general, 1: fast (first form), 2: fast per-step, 3: block mode (one report per block of
+// `gap` steps), 4: block-sub mode (blocks of `rep` steps, reports every `gap` steps inside them).
+// Mirrors run_member/run_timeline of smart_kernels.cu for one member, summary or raw reporting.
+static int emulate(int mode, int rep, double area, double dt, long T, long W, const double *rain,
+                   const double *peva, const double *par, int has_extra, double aar_ro,
+                   const double *split, int report_type, int gap, double *discharge, double *gw_out)
 {
     typedef double R;
     const double Tt = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
@@ -67,6 +68,41 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
     for (long seg = 0; seg < 2; ++seg) {
         long n = seg == 0 ? W : T;
         if (seg == 1) { countdown = (int)(T - (n_rep - 1) * gap); r = 0; acc = agw = aall = 0; GN = GD = 0; riv0 = s.riv; }
+        if (mode == 4) {   // block-sub mode: kModeBlockSub of run_timeline
+            const bool summary = report_type == 1 || gap == 1;
+            if (seg == 1) countdown = gap;
+            for (long day = 0; day < n / rep; ++day) {
+                const double ex_d = __dsub_rn(__dmul_rn(rain[day * rep], Tt), peva[day * rep]);
+                const BlockPar<R> bp = block_par<R, 1>(kc);
+                const R r_rk = kc[6];
+                const bool wet = ex_d >= 0.0;
+                const R ex = wet ? ex_d : 0.0, hex = fp.Hz * ex;
+                if (wet) {
+                    if (!carry.valid) { carry.tot = soil_total(s); carry.valid = true; }
+                } else {
+                    dry_block_soil<R>(s, kc[0], ex_d, rep);
+                    carry.valid = false;
+                }
+                for (int h = 0; h < rep; ++h) {
+                    const R q_riv = s.riv * r_rk;
+                    R q_gw, q_in;
+                    if (wet) fast_wet_hour<R, 1>(s, fp, kc, bp, carry, ex, hex, 1u, q_gw, q_in);
+                    else fast_dry_hour<R, 1>(s, fp, kc, bp, q_gw, q_in);
+                    acc += q_riv;
+                    if (summary) agw += q_gw;
+                    if (--countdown == 0) {
+                        countdown = gap;
+                        const R sval = (summary ? acc : q_riv) * (summary ? mean_scale : qscale);
+                        if (summary) aall += acc; else { agw += q_gw; aall += q_in; }
+                        acc = 0;
+                        if (seg == 1) discharge[r++] = sval;
+                    }
+                }
+            }
+            if (seg == 1) { *gw_out = summary ? agw / (aall + (s.riv - riv0)) : agw / aall; return 0; }
+            riv0 = s.riv; acc = 0; agw = 0; aall = 0;
+            continue;
+        }
         if (mode == 3) {   // block mode: forcing constant inside aligned blocks of `gap` steps
             for (long day = 0; day < n / gap; ++day) {
                 const double ex_d = __dsub_rn(__dmul_rn(rain[day * gap], Tt), peva[day * gap]);
@@ -93,4 +129,20 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
     }
     *gw_out = GN / GD;
     return 0;
+}
+
+extern "C" int emulate_run(int mode, double area, double dt, long T, long W, const double *rain,
+                           const double *peva, const double *par, int has_extra, double aar_ro,
+                           const double *split, int report_type, int gap, double *discharge, double *gw_out)
+{
+    return emulate(mode, gap, area, dt, T, W, rain, peva, par, has_extra, aar_ro, split, report_type, gap, discharge,
+                   gw_out);
+}
+
+// block-sub mode: forcing constant inside aligned blocks of `rep` steps, reports every `gap` steps
+extern "C" int emulate_run_sub(int rep, double area, double dt, long T, long W, const double *rain,
+                               const double *peva, const double *par, int has_extra, double aar_ro,
+                               const double *split, int report_type, int gap, double *discharge, double *gw_out)
+{
+    return emulate(4, rep, area, dt, T, W, rain, peva, par, has_extra, aar_ro, split, report_type, gap, discharge, gw_out);
 }
