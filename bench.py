@@ -91,7 +91,23 @@ def lhs_rows(n, seed):
     return latin_hypercube(n, [p.ranges[name] for name in p.names], rng=rng)
 
 
-def make_workload(name, rank, members=None):
+def simulate_on_device(w, params):
+    """Daily discharge of ONE parameter set on workload w's forcing, through the CUDA path (used to
+    build synthetic observations; the CPU arm passes the oracle's run instead)."""
+    from smartpy_b200.engine import BatchEngine
+    eng = BatchEngine(w["rain"], w["peva"], w["area"], w["dt"], w["gap"], extra=w["extra"],
+                      warm_up_steps=w["warm_steps"], report=w["report"])
+    return eng.run(np.asarray(params)[None, :], discharge=True, scores=False, gw=False)["discharge"][:, 0].cpu().numpy()
+
+
+def simulate_on_host(w, params):
+    """Same with the CPU oracle (bench.py's reference arm / cpu_baseline only)."""
+    import oracle
+    return oracle.run(w["area"], w["dt"], w["rain"], w["peva"], params, w["extra"], w["n_steps"], w["gap"],
+                      report=w["report"], warm_up=w["warm_steps"] * w["dt"] / 86400.0)[0]
+
+
+def make_workload(name, rank, members=None, simulate=simulate_on_device):
     """-> dict(rain, peva, area, obs, dt, gap, warm_steps, params, label, discharge, mpc)."""
     golden = os.path.join(ROOT, "tests", "golden")
     w = dict(dt=3600.0, gap=24, warm_steps=8760, extra=EXTRA, gwc=0.12667, discharge=False, mpc=None,
@@ -105,10 +121,15 @@ def make_workload(name, rank, members=None):
     elif name == "c3":
         n_days = 10958
         rain, peva = synthetic_forcing(n_days)
+        w.update(rain=rain, peva=peva, area=175.46e6)
+        # observations = a run of the reference's test parameter file on this forcing
+        # x exp(N(0, 0.1^2)) daily noise, 12 % of the days missing (seed + 1)
+        p_test = np.load(os.path.join(golden, "runs_single.npz"))["p_test"]
+        q = simulate(dict(w, n_steps=rain.shape[0]), p_test)
         rng = np.random.Generator(np.random.PCG64(20260102))
-        obs = np.abs(rng.normal(5.0, 3.0, n_days))
+        obs = q * np.exp(rng.normal(0.0, 0.1, n_days))
         obs[rng.random(n_days) < 0.12] = np.nan
-        w.update(rain=rain, peva=peva, obs=obs, area=175.46e6)
+        w.update(obs=obs)
         n = members or 1250000
         w["label"] = "LHS {} parameter sets per GPU x 30 yr hourly synthetic forcing (262992 + 8760 steps), scores only".format(n)
     elif name in ("c4a", "c4b"):
@@ -575,7 +596,7 @@ def reference_arm(args, rank, world):
     """The reference's CPU algorithm on all host cores (rank 0 only)."""
     if rank != 0:
         return
-    w = make_workload(args.workload, 0, args.members)
+    w = make_workload(args.workload, 0, args.members, simulate=simulate_on_host)
     pool, cores = make_pool(w)
     times, sample = [], ""
     for i in range(args.warmup + args.steps):

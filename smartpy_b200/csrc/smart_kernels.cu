@@ -147,6 +147,7 @@ struct KArgs {
     int C, mpc, gap, report_type;
     int chunk, kc, use_tma, force_general;
     int has_extra, best_col, best_sign, first_report;
+    int skew, skew_groups;       // start delay of a CTA in cycles per group step, number of groups (0 = none)
     int rep, mode;               // steps per forcing row (1 = one row per step); kModeStep / kModeBlock / kModeBlockSub
     double dt, aar_ro, split[5], gw_constraint;
 };
@@ -775,12 +776,27 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         // (single catchment, no [t][member] output: validate().)  Idle slots hold -1; an idle thread
         // shadows the member of its CTA's first thread, a CTA whose first slot is idle has no member.
         const long long first = a.order[static_cast<long long>(blockIdx.x) * BLOCK];
-        if (first < 0) return;
+        if (first < 0) {
+            if (a.best_sign != 0 && tid == 0) {     // no candidate from this CTA
+                a.blk_best_score[blockIdx.x] = -CUDART_INF;
+                a.blk_best_index[blockIdx.x] = 0x7fffffffffffffffLL;
+            }
+            return;
+        }
         m = a.order[m];
         if (m < 0) {
             active = false;
             m = first;
         }
+    }
+
+    if (a.skew > 0) {
+        // Every member of a single-catchment batch walks the SAME forcing: CTAs that start together
+        // reach the dry days (closed form, scoring: little FP64 work) and the wet days (FP64-pipe
+        // bound) together, so the sub-partition alternates between an idle and a contended pipe.
+        // CTAs that share an SM start a few days' worth of cycles apart instead.
+        const long long until = clock64() + static_cast<long long>((blockIdx.x / 148) % a.skew_groups) * a.skew;
+        while (clock64() < until) __nanosleep(2000);
     }
 
     double par[SMART_N_PARAMS];
@@ -1092,6 +1108,12 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     const int block = block_of(d);
     const int blocks = n_blocks_of(d, block);
     const int mode = mode_of(d);
+    {
+        static const int skew = [] { const char *e = getenv("SMART_B200_SKEW"); return e ? atoi(e) : 0; }();
+        static const int groups = [] { const char *e = getenv("SMART_B200_SKEW_GROUPS"); return e ? atoi(e) : 12; }();
+        a.skew = skew;
+        a.skew_groups = groups > 0 ? groups : 1;
+    }
     const bool daily = mode != kModeStep;
     a.mode = mode;
     a.rep = daily ? d->forcing_repeat : 1;

@@ -341,24 +341,31 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
         carry.tot = tot3;
         carry.valid = true;
     } else {
+        // binary32 state: what a pass takes out of a layer is read back as the difference of the
+        // layer before and after (exact: the two values are within a factor of two), so that the
+        // water handed to the stores is EXACTLY the water the soil lost.  Forming the leak, adding it
+        // to the inflow and subtracting it from the layer rounds the subtraction to the layer's ulp
+        // (2e-6 mm for an 18 mm layer, against leaks of 1e-3 mm per hour), and in a saturated column
+        // under constant forcing that rounding is the same every hour: a mass-balance bias of up to
+        // 5e-4 of the leak, |dNSE| up to 2.3e-5 over an LHS sample (profiles/r02_fp32_*.json).
         in_gw = zero;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const R leak = s.ly[i] * pw[i];
-            in_int += leak;
-            s.ly[i] -= leak;
+            const R nl = fma(-s.ly[i], pw[i], s.ly[i]);
+            in_int += s.ly[i] - nl;
+            s.ly[i] = nl;
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const R leak = s.ly[i] * (i == 0 ? sp : sp * inv_const<R>(i));
-            in_gw += leak;
-            s.ly[i] -= leak;
+            const R nl = fma(-s.ly[i], i == 0 ? sp : sp * inv_const<R>(i), s.ly[i]);
+            in_gw += s.ly[i] - nl;
+            s.ly[i] = nl;
         }
 #pragma unroll
         for (int i = 5; i >= 0; --i) {
-            const R leak = s.ly[i] * pw[5 - i];
-            in_gw += leak;
-            s.ly[i] -= leak;
+            const R nl = fma(-s.ly[i], pw[5 - i], s.ly[i]);
+            in_gw += s.ly[i] - nl;
+            s.ly[i] = nl;
         }
         carry.valid = false;
     }

@@ -34,28 +34,82 @@ def shard_bounds(n_rows, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def all_gather_rows(scores, gw, n_rows):
-    """All-gather the per-rank [n_r, 8] scores and [n_r] gw blocks into [n_rows, 8] / [n_rows]
-    on every rank (ragged shards are padded to the largest block)."""
+def _backend_device(like=None):
+    """The device collectives of the current backend work on: the caller's CUDA device under
+    NCCL, the host under gloo."""
+    import torch
+    dist = _dist()
+    if dist.get_backend() == 'nccl':
+        if like is not None and like.is_cuda:
+            return like.device
+        return torch.device('cuda', torch.cuda.current_device())
+    return torch.device('cpu')
+
+
+def broadcast_rows(rows, src=0):
+    """The [N, k] float64 array of rank `src`, on every rank (a numpy array in, a numpy array out).
+    Used to give a sharded Monte Carlo run ONE sample: each rank draws its own from numpy's global
+    generator at construction, rank 0's is the one that counts."""
+    import numpy as np
+    import torch
+    dist = _dist()
+    rank, world = rank_world()
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    if world == 1:
+        return rows
+    dev = _backend_device()
+    shape = torch.tensor(list(rows.shape), dtype=torch.int64, device=dev)
+    dist.broadcast(shape, src=src)
+    buf = torch.from_numpy(rows).to(dev) if rank == src else torch.empty(tuple(shape.tolist()), dtype=torch.float64, device=dev)
+    dist.broadcast(buf, src=src)
+    return buf.cpu().numpy()
+
+
+def all_gather_rows(block, n_rows):
+    """All-gather the per-rank row blocks [n_r, w] (rank r holds the rows shard_bounds(n_rows, r,
+    world)) into the full [n_rows, w] table on every rank; ragged shards are padded to the largest
+    block.  One collective (NCCL all-gather over NVLink on the GPU box)."""
     import torch
     dist = _dist()
     rank, world = rank_world()
     if world == 1:
-        return scores, gw
+        return block
+    dev = _backend_device(block)
+    block = block.to(dev)
     biggest = shard_bounds(n_rows, 0, world)[1]
-    width = scores.shape[1] + 1
-    block = torch.full((biggest, width), float('nan'), dtype=torch.float64, device=scores.device)
-    block[:scores.shape[0], :-1] = scores
-    block[:gw.shape[0], -1] = gw
-    gathered = torch.empty((world * biggest, width), dtype=torch.float64, device=scores.device)
-    dist.all_gather_into_tensor(gathered, block)
+    width = block.shape[1]
+    if block.shape[0] == biggest and block.is_contiguous():
+        padded = block
+    else:
+        padded = torch.full((biggest, width), float('nan'), dtype=block.dtype, device=dev)
+        padded[:block.shape[0]] = block
+    gathered = torch.empty((world * biggest, width), dtype=block.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, padded)
+    if n_rows == world * biggest:
+        return gathered
     gathered = gathered.view(world, biggest, width)
-    parts = []
-    for r in range(world):
-        lo, hi = shard_bounds(n_rows, r, world)
-        parts.append(gathered[r, :hi - lo])
-    full = torch.cat(parts)
-    return full[:, :-1].contiguous(), full[:, -1].contiguous()
+    return torch.cat([gathered[r, :shard_bounds(n_rows, r, world)[1] - shard_bounds(n_rows, r, world)[0]]
+                      for r in range(world)])
+
+
+def send_rows_to_first(rows, owner, n_rows):
+    """Collective: the [n_rows, w] block held by rank `owner` arrives on rank 0 (returned there;
+    other ranks get None).  Every rank calls it with its own block; only `owner`'s is used."""
+    import torch
+    dist = _dist()
+    rank, world = rank_world()
+    if world == 1 or owner == 0:
+        return rows if rank == 0 else None
+    dev = _backend_device(rows)
+    width = int(rows.shape[1])
+    if rank == owner:
+        dist.send(rows.to(dev).contiguous(), dst=0)
+        return None
+    if rank == 0:
+        buf = torch.empty((n_rows, width), dtype=rows.dtype, device=dev)
+        dist.recv(buf, src=owner)
+        return buf
+    return None
 
 
 def all_gather_best(best_score, best_index, first_row, sign=1):

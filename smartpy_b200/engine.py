@@ -344,11 +344,13 @@ class BatchEngine(object):
             buf = self._staging[name] = torch.empty(tuple(shape), dtype=dtype).pin_memory()
         return buf
 
-    def run_host(self, params, discharge=False, gw=True):
+    def run_host(self, params, discharge=False, gw=True, copy=False):
         """params: numpy [N, 10] on the host -> dict of numpy arrays on the host ('scores' [N, 8] when
         the engine has observations, 'gw' [N], 'discharge' [n_report, N] on request).  The copies go
         through pinned staging buffers the engine keeps from call to call (no pin_memory() or
-        allocation on the steady path) and the call returns when the results are in host memory."""
+        allocation on the steady path) and the call returns when the results are in host memory.
+        The returned arrays are VIEWS of that staging memory: they are overwritten by the next
+        run_host() of this engine; pass copy=True (or copy them) to keep them longer."""
         torch = _torch()
         dev = self.device
         p_host = np.ascontiguousarray(params, dtype=np.float64)
@@ -378,6 +380,8 @@ class BatchEngine(object):
             out['gw'] = table[:, _native.N_SCORES]
         if discharge:
             out['discharge'] = q_pin.numpy()
+        if copy:
+            out = {k: v.copy() for k, v in out.items()}
         return out
 
     def _device_buffer(self, name, shape):

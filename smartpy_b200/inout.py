@@ -13,16 +13,14 @@ import argparse
 
 import numpy as np
 
-try:
-    from netCDF4 import Dataset
-except ImportError:
-    Dataset = None
-
 from .timeframe import (
     check_interval_in_seconds, get_required_resolution, rescale_regular_cumulative_grid,
     rescale_irregular_mean_grid, to_seconds, from_seconds)
-from .version import __version__
 
+# NetCDF: the reference reads/writes it through the optional package netCDF4 and raises these
+# messages when the package is missing (inout.py:212-231, :299-310).  That package is outside this
+# hot path's scope and not part of the image, so 'netcdf' always takes the
+# reference's "package missing" exit here; 'csv' is the supported format.
 _NETCDF_IN = ("The use of 'netcdf' as the input file format requires the package 'netCDF4', "
               "please install it and retry, or choose another file format.")
 _NETCDF_OUT = ("The use of 'netcdf' as the output file format requires the package 'netCDF4', "
@@ -81,26 +79,6 @@ def read_csv_flow_arrays(csv_file, key_header, val_header):
     return _parse_stamps(keys), np.array(vals, dtype=np.float64)
 
 
-def read_netcdf_series_arrays(netcdf_file, key_variable, val_variable, drop_nan=False):
-    if not Dataset:
-        raise Exception(_NETCDF_IN)
-    try:
-        with Dataset(netcdf_file, "r") as handle:
-            handle.set_auto_mask(False)
-            try:
-                stamps = np.asarray(handle.variables[key_variable][:]).astype(np.int64)
-                values = np.asarray(handle.variables[val_variable][:])
-            except KeyError:
-                raise Exception('Variable {} or {} does not exist in {}.'.format(key_variable, val_variable,
-                                                                                 netcdf_file))
-    except IOError:
-        raise Exception('File {} could not be found.'.format(netcdf_file))
-    if drop_nan:
-        keep = ~np.isnan(values)
-        stamps, values = stamps[keep], values[keep]
-    return stamps, values
-
-
 def _as_dict(stamps, values, ordered=False):
     out = OrderedDict() if ordered else dict()
     for s, v in zip(stamps.tolist(), values):
@@ -115,50 +93,30 @@ def read_csv_time_series_with_delta_check(csv_file, key_header, val_header):
     return _as_dict(stamps, values), from_seconds(first), from_seconds(last), timedelta(seconds=step)
 
 
-def read_netcdf_time_series_with_delta_check(netcdf_file, key_variable, val_variable):
-    stamps, values = read_netcdf_series_arrays(netcdf_file, key_variable, val_variable)
-    first, last, step = check_interval_in_seconds(stamps, netcdf_file)
-    return _as_dict(stamps, values), from_seconds(first), from_seconds(last), timedelta(seconds=step)
-
-
 def read_csv_time_series_with_missing_check(csv_file, key_header, val_header):
     return _as_dict(*read_csv_flow_arrays(csv_file, key_header, val_header), ordered=True)
 
 
-def read_netcdf_time_series_with_missing_check(netcdf_file, key_variable, val_variable):
-    return _as_dict(*read_netcdf_series_arrays(netcdf_file, key_variable, val_variable, drop_nan=True),
-                    ordered=True)
-
-
 def _read_forcing_arrays(file_location, file_format, name):
     if file_format == 'netcdf':
-        if not Dataset:
-            raise Exception(_NETCDF_IN)
-        return read_netcdf_series_arrays(file_location, 'DateTime', name)
+        raise Exception(_NETCDF_IN)
     return read_csv_series_arrays(file_location, 'DateTime', name)
 
 
 def read_rain_file(file_location, file_format):
     if file_format == 'netcdf':
-        if Dataset:
-            return read_netcdf_time_series_with_delta_check(file_location, key_variable='DateTime', val_variable='rain')
         raise Exception(_NETCDF_IN)
     return read_csv_time_series_with_delta_check(file_location, key_header='DateTime', val_header='rain')
 
 
 def read_peva_file(file_location, file_format):
     if file_format == 'netcdf':
-        if Dataset:
-            return read_netcdf_time_series_with_delta_check(file_location, key_variable='DateTime', val_variable='peva')
         raise Exception(_NETCDF_IN)
     return read_csv_time_series_with_delta_check(file_location, key_header='DateTime', val_header='peva')
 
 
 def read_flow_file(file_location, file_format):
     if file_format == 'netcdf':
-        if Dataset:
-            return read_netcdf_time_series_with_missing_check(file_location,
-                                                              key_variable='DateTime', val_variable='flow')
         raise Exception(_NETCDF_IN)
     return read_csv_time_series_with_missing_check(file_location, key_header='DateTime', val_header='flow')
 
@@ -194,9 +152,8 @@ def get_dict_peva_series_simu(file_location, file_format, start_simu, end_simu, 
 def get_discharge_series(file_location, file_format, start_report, end_report, catchment_area, gauged_area):
     """Array form of get_dict_discharge_series (inout.py:61-78): float64[n_report], NaN = missing."""
     if file_format == 'netcdf':
-        stamps, values = read_netcdf_series_arrays(file_location, 'DateTime', 'flow', drop_nan=True)
-    else:
-        stamps, values = read_csv_flow_arrays(file_location, 'DateTime', 'flow')
+        raise Exception(_NETCDF_IN)
+    stamps, values = read_csv_flow_arrays(file_location, 'DateTime', 'flow')
     scaling_factor = catchment_area / gauged_area
     # calendar-day window: two days before the first report stamp, one day after the last
     day = stamps // 86400
@@ -266,10 +223,7 @@ def get_dict_simulation_settings(file_location):
 # ------------------------------------------------------------------ writers
 def write_flow_file_from_nds(series_report, discharge, the_file, out_file_format, parallel=False):
     if out_file_format == 'netcdf':
-        if Dataset:
-            write_flow_netcdf_file_from_nds(series_report, discharge, the_file, parallel=parallel)
-        else:
-            raise Exception(_NETCDF_OUT)
+        raise Exception(_NETCDF_OUT)
     elif out_file_format == 'csv':
         write_flow_csv_file_from_nds(series_report, discharge, the_file)
     else:
@@ -284,22 +238,8 @@ def write_flow_csv_file_from_nds(series_report, discharge, csv_file):
         out.writerows((dt, '%e' % val) for dt, val in zip(series_report, discharge))
 
 
-def write_flow_netcdf_file_from_nds(series_report, discharge, netcdf_file, parallel):
-    with Dataset(netcdf_file + '.nc', 'w', format='NETCDF4', parallel=parallel) as handle:
-        handle.description = "Discharge file generated with SMARTpy v{}.".format(__version__)
-        handle.createDimension('DateTime', len(series_report))
-        t = handle.createVariable("DateTime", np.float64, ('DateTime',))
-        t.units = 'seconds since 1970-01-01 00:00:00.0'
-        handle.createVariable('flow', np.float32, ('DateTime',))
-        handle.variables['DateTime'][0:len(series_report)] = np.array(
-            [to_seconds(dt) for dt in series_report], dtype=np.float64)
-        handle.variables['flow'][0:len(series_report)] = discharge
-
-
 def valid_file_format(fmt):
     if fmt.lower() == "netcdf":
-        if Dataset:
-            return "netcdf"
         raise argparse.ArgumentTypeError("NetCDF4 module is not installed, please choose another file format.")
     elif fmt.lower() == "csv":
         return "csv"

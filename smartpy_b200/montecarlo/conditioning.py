@@ -6,8 +6,10 @@ The reference conditions a sample after a round trip through a float32 text/NetC
 selections are two calls into the CUDA library: ``smart_condition_rows`` (predicate mask +
 ordered compaction) and ``smart_best_rows`` (radix select of the k best + sort of those k only),
 ``include/smart_b200.h``.  They follow the reference's rules, including its order (ascending,
-best last), numpy's NaN-sorts-last rule and the literal 'outside' rule.  CUDA tensors only:
-the file-based GLUE/Best classes keep the numpy rules (``montecarlo.condition_mask``).
+best last), numpy's NaN-sorts-last rule and the literal 'outside' rule.  ``Best.from_run`` /
+``GLUE.from_run`` use them on the score table of a run that is still in memory; the file-based
+constructors (sample read back as float32 from the database) use the numpy form of the same
+rules, ``condition_mask``.
 """
 import numpy as np
 
@@ -19,27 +21,54 @@ def _torch():
     return torch
 
 
-def _conditions(columns, conditions_val, conditions_typ):
-    """(kind, values) conditions -> ctypes array of smart_condition; same checks and messages as
-    glue.py:246-286."""
-    if len(columns) > _native.MAX_CONDITIONS:
-        raise Exception("At most {} conditions can be combined.".format(_native.MAX_CONDITIONS))
-    conds = (_native.Condition * max(1, len(columns)))()
-    for i, (col, values, kind) in enumerate(zip(columns, conditions_val, conditions_typ)):
+def parse_conditions(conditions_val, conditions_typ):
+    """[(kind, lo, hi)] from the reference's (values tuple, kind) pairs, with the reference's checks and
+    messages (glue.py:246-286, best.py:243-277): 'equal' / 'min' / 'max' take one value, 'inside' /
+    'outside' two increasing ones."""
+    parsed = []
+    for values, kind in zip(conditions_val, conditions_typ):
         if kind in ('equal', 'min', 'max'):
             if len(values) != 1:
                 raise Exception("The tuple for \"{}\" condition does not contain one and only one "
                                 "element.".format(kind))
-            lo, hi = float(values[0]), 0.0
+            parsed.append((kind, float(values[0]), 0.0))
         elif kind in ('inside', 'outside'):
             if len(values) != 2:
                 raise Exception("The tuple for \"{}\" condition does not contain two and only two "
                                 "elements.".format(kind))
             if not values[1] > values[0]:
                 raise Exception("The two elements of the tuple for \"{}\" are inconsistent.".format(kind))
-            lo, hi = float(values[0]), float(values[1])
+            parsed.append((kind, float(values[0]), float(values[1])))
         else:
             raise Exception("The type of threshold \"{}\" is not in the database.".format(kind))
+    return parsed
+
+
+_HOST_RULES = {
+    'equal': lambda x, lo, hi: x == lo,
+    'min': lambda x, lo, hi: x >= lo,
+    'max': lambda x, lo, hi: x <= lo,
+    'inside': lambda x, lo, hi: (x >= lo) & (x <= hi),
+    'outside': lambda x, lo, hi: (x <= lo) & (x >= hi),      # the reference's literal rule (glue.py:278)
+}
+
+
+def condition_mask(obj_fns, conditions_val, conditions_typ):
+    """Host form (numpy) of the selection rules, for the sample read back from a database file:
+    boolean mask over the rows of obj_fns[N, k], one (values, kind) condition per column (thresholds
+    enter the comparisons as Python floats, as in the reference)."""
+    mask = np.ones((obj_fns.shape[0],), dtype=bool)
+    for column, (kind, lo, hi) in zip(obj_fns.T, parse_conditions(conditions_val, conditions_typ)):
+        mask &= _HOST_RULES[kind](column, lo, hi)
+    return mask
+
+
+def _conditions(columns, conditions_val, conditions_typ):
+    """ctypes array of smart_condition for the device kernels."""
+    if len(columns) > _native.MAX_CONDITIONS:
+        raise Exception("At most {} conditions can be combined.".format(_native.MAX_CONDITIONS))
+    conds = (_native.Condition * max(1, len(columns)))()
+    for i, (col, (kind, lo, hi)) in enumerate(zip(columns, parse_conditions(conditions_val, conditions_typ))):
         conds[i] = _native.Condition(int(col), _native.COND_KINDS[kind], lo, hi)
     return conds
 

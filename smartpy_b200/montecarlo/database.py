@@ -1,0 +1,95 @@
+"""The sample database of a Monte Carlo run -- the on-disk format of the reference
+(``smartpy/montecarlo/montecarlo.py:90-127`` header, ``:211-231`` rows, ``:155-177`` compression,
+``:233-262`` reader), written and read in bulk.
+
+Format ('csv'): one header line ``obj_fn_names + param_names + report stamps`` and one line per
+sample with every value printed as ``'%.6e'`` of its float32 rounding.  The reference appends one
+line per simulation from inside spotpy's loop and reads the file back through ``csv.DictReader``
+row by row; here a whole batch of rows is formatted at once and the reader pulls the wanted
+columns (looked up BY NAME in the header, as the reference does, so older files with extra columns
+still load) straight into float32 arrays.
+
+'netcdf' needs the optional package netCDF4 in the reference and raises when it is missing; that
+package is outside this path's scope, so 'netcdf' always takes that exit here (see inout.py).
+"""
+import gzip
+import io
+import os
+import shutil
+
+import numpy as np
+
+NETCDF_MESSAGE = ("The use of 'netcdf' as the output file format requires the package 'netCDF4', "
+                  "please install it and retry, or choose another file format.")
+
+
+def database_path(out_folder, catchment, func, out_format):
+    """``<out>/<catchment>.SMART.<func>`` (+ ``.nc`` for netcdf), montecarlo.py:79-82."""
+    stem = '{}{}.SMART.{}'.format(out_folder, catchment, func)
+    return stem + '.nc' if out_format == 'netcdf' else stem
+
+
+class SampleDatabase(object):
+    """Writer.  ``open()`` -> header; ``write_rows()`` any number of times, rows in sample order;
+    ``close(compression)`` -> optional gzip (``<file>.gz`` replaces the file, as the reference)."""
+
+    def __init__(self, path, out_format, columns, stamps=()):
+        if out_format == 'netcdf':
+            raise Exception(NETCDF_MESSAGE)
+        if out_format != 'csv':
+            raise Exception("The output format type '{}' cannot be written by SMARTpy, "
+                            "choose from: 'csv', 'netcdf'.".format(out_format))
+        self.path = path
+        self.header = list(columns) + [dt.strftime('%Y-%m-%d %H:%M:%S') for dt in stamps]
+        self.n_series = len(stamps)
+        self._handle = None
+        self.rows_written = 0
+
+    def open(self):
+        self._handle = io.open(self.path, 'w', newline='', encoding='utf8')
+        self._handle.write(','.join(self.header) + '\n')
+        return self
+
+    def write_rows(self, obj_fns, parameters, simulations=None):
+        """obj_fns [n, k], parameters [n, 10] (+ simulations [n, n_report] when the run keeps them)."""
+        blocks = [np.asarray(obj_fns), np.asarray(parameters)]
+        if self.n_series:
+            if simulations is None or np.asarray(simulations).shape[1] != self.n_series:
+                raise ValueError("the database keeps the simulated series: simulations [n, {}] required".format(
+                    self.n_series))
+            blocks.append(np.asarray(simulations))
+        table = np.concatenate(blocks, axis=1).astype(np.float32)    # '%.6e' of the float32 value, montecarlo.py:226-231
+        np.savetxt(self._handle, table, fmt='%.6e', delimiter=',')
+        self.rows_written += table.shape[0]
+
+    def close(self, compression=None):
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+        if compression is True:
+            with io.open(self.path, 'rb') as plain, gzip.open(self.path + '.gz', 'wb') as packed:
+                shutil.copyfileobj(plain, packed)
+            os.remove(self.path)
+
+
+def read_sample_database(path, out_format, param_names, obj_fn_names, gzipped=False):
+    """-> (parameters float32 [N, 10], objective functions float32 [N, k]) of a database written
+    by a previous run (montecarlo.py:233-262): columns are found by name in the header."""
+    if out_format == 'netcdf':
+        raise Exception(NETCDF_MESSAGE)
+    opener = (lambda: gzip.open(path + '.gz', 'rt', encoding='utf8')) if gzipped else \
+        (lambda: io.open(path, 'r', encoding='utf8'))
+    with opener() as handle:
+        header = handle.readline().rstrip('\r\n').split(',')
+        try:
+            wanted = [header.index(name) for name in list(param_names) + list(obj_fn_names)]
+        except ValueError as missing:
+            raise KeyError(str(missing))                       # DictReader's row[name] raises KeyError
+        # text -> binary64 -> float32, the conversion np.array(list_of_strings, dtype=float32) makes
+        table = np.loadtxt(handle, delimiter=',', usecols=sorted(set(wanted)), dtype=np.float64, ndmin=2)
+    position = {col: k for k, col in enumerate(sorted(set(wanted)))}
+    table = table.astype(np.float32)
+    n_par = len(param_names)
+    params = table[:, [position[c] for c in wanted[:n_par]]]
+    obj_fns = table[:, [position[c] for c in wanted[n_par:]]]
+    return np.ascontiguousarray(params), np.ascontiguousarray(obj_fns)

@@ -1,116 +1,68 @@
-"""Monte Carlo base class -- same surface as the reference's
+"""Monte Carlo base class -- the caller of the hot path.  Same surface as the reference's
 ``smartpy/montecarlo/montecarlo.py:43-262`` (constructor arguments, ``run(compression)``, the
-spotpy-protocol methods ``parameters / simulation / evaluation / objectivefunction / save``,
-the sample database formats), but ``run()`` does not iterate sample by sample through
-spotpy (montecarlo.py:153-154): the whole sample goes through ONE kernel launch per batch
-with the objective functions fused (``BatchEngine.run``), and the database is written in
-bulk.  spotpy is therefore not required; ``parallel='mpi'`` is accepted for signature
-compatibility and mapped onto ``torch.distributed`` when a process group is initialised
-(rows are sharded over ranks, scores all-gathered over NCCL).
+spotpy-protocol methods ``parameters / simulation / evaluation / objectivefunction / save``, the
+sample database format), different engine: ``run()`` does not iterate sample by sample through
+spotpy (montecarlo.py:153-154).  The whole sample goes through ONE kernel launch per batch with
+the objective functions fused (``BatchEngine.run``) and the database is written in bulk
+(``database.SampleDatabase``).  spotpy is therefore not required.  ``parallel='mpi'`` keeps its
+meaning of "several processes share the sample", mapped onto ``torch.distributed``: rows are
+sharded over the ranks of the process group, the scores all-gathered (NCCL on the GPU box).
 """
-from csv import DictReader
-import gzip
-from io import open
-from os import sep, remove, rename
-import shutil
+from os import sep
 
 import numpy as np
-
-try:
-    from netCDF4 import Dataset
-except ImportError:
-    Dataset = None
 
 from ..smart import SMART
 from ..inout import get_dict_simulation_settings
 from ..objfunctions import groundwater_constraint
-from ..version import __version__
 from .. import distributed as dist_utils
+from .conditioning import condition_mask  # noqa: F401  (re-exported: the host form of the selection rules)
+from .database import SampleDatabase, database_path, read_sample_database
 
-_NETCDF_OUT = ("The use of 'netcdf' as the output file format requires the package 'netCDF4', "
-               "please install it and retry, or choose another file format.")
+SCORE_COLUMNS = ('NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE')
 
 # members per kernel launch when the simulated series are kept (bounds device memory:
 # n_report x batch x 8 B); scores-only runs go in one launch
 _SAVE_SIM_BATCH = 1 << 16
 
 
-def condition_mask(obj_fns, conditions_val, conditions_typ):
-    """Boolean mask over the rows of obj_fns[N, k] for k (kind, values) conditions -- the
-    selection rules shared by GLUE (glue.py:246-286) and Best (best.py:243-277)."""
-    mask = np.ones((obj_fns.shape[0],), dtype=bool)
-    for column, values, kind in zip(obj_fns.T, conditions_val, conditions_typ):
-        if kind in ('equal', 'min', 'max'):
-            if len(values) != 1:
-                raise Exception("The tuple for \"{}\" condition does not contain one and only one "
-                                "element.".format(kind))
-            if kind == 'equal':
-                selection = column == values[0]
-            elif kind == 'min':
-                selection = column >= values[0]
-            else:
-                selection = column <= values[0]
-        elif kind in ('inside', 'outside'):
-            if len(values) != 2:
-                raise Exception("The tuple for \"{}\" condition does not contain two and only two "
-                                "elements.".format(kind))
-            if not values[1] > values[0]:
-                raise Exception("The two elements of the tuple for \"{}\" are inconsistent.".format(kind))
-            if kind == 'inside':
-                selection = (column >= values[0]) & (column <= values[1])
-            else:
-                selection = (column <= values[0]) & (column >= values[1])   # as written at glue.py:278
-        else:
-            raise Exception("The type of threshold \"{}\" is not in the database.".format(kind))
-        mask &= selection
-    return mask
-
-
 class MonteCarlo(object):
     def __init__(self, catchment, root_f, in_format, out_format,
                  parallel, save_sim, func, settings_filename):
-        in_f = sep.join([root_f, 'in', catchment, sep])
-
-        # collect the simulation information from the .sttngs file
-        settings_file = ''.join([in_f, settings_filename if settings_filename else catchment + '.sttngs'])
-        c_area, g_area, start, end, delta_simu, delta_report, warm_up, gw_constraint = \
-            get_dict_simulation_settings(settings_file)
-
-        # generate an instance of the SMART model class
-        self.model = SMART(catchment, c_area, start, end, delta_simu, delta_report, warm_up,
-                           in_format, out_format, root_f,
-                           g_area)
-
-        # set the technical aspects of the simulation
+        # where this experiment lives (kept so that Best / GLUE .from_run can set up a sibling)
+        self.catchment, self.root_f = catchment, root_f
+        self.in_format, self.out_format = in_format, out_format
+        self.settings_filename = settings_filename
+        self.func = func
         self.parallel = parallel
-        self.p = True if parallel == 'mpi' else False
+        self.p = parallel == 'mpi'
         self.save_sim = save_sim
 
-        # possible additional constraint for SMART on the portion of base flow in runoff
+        # the simulation period and catchment description come from the .sttngs file
+        settings_file = sep.join([root_f, 'in', catchment, '']) + (settings_filename or catchment + '.sttngs')
+        (area, gauged_area, start, end, delta_simu, delta_report,
+         warm_up, gw_constraint) = get_dict_simulation_settings(settings_file)
+        self.model = SMART(catchment, area, start, end, delta_simu, delta_report, warm_up,
+                           in_format, out_format, root_f, gauged_area)
+
+        # objective functions: the seven scores, plus the groundwater constraint when the
+        # settings give one (montecarlo.py:66-74)
         self.constraints = {'gw': gw_constraint}
-
         self.param_names = self.model.parameters.names
-        self.obj_fn_names = \
-            ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW'] \
-            if self.constraints['gw'] else \
-            ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE']
+        self.obj_fn_names = list(SCORE_COLUMNS) + (['GW'] if gw_constraint else [])
 
-        # the sample: sub-classes set sample_params [N, 10]; p_map / params kept for compatibility
+        # the sample: sub-classes register it with _set_sample()
         self.sample_params = None
         self.p_map = None
         self.params = None
 
-        # database
-        self.out_format = out_format
-        self.db_file = \
-            self.model.out_f + '{}.SMART.{}.nc'.format(catchment, func) if self.out_format == 'netcdf' else \
-            self.model.out_f + '{}.SMART.{}'.format(catchment, func)
+        self.db_file = database_path(self.model.out_f, catchment, func, out_format)
         self.database = None
         self.precision = 'f64'
-        #: device tensors of the last run: 'scores' [N, n_obj_fns], 'gw' [N] (and 'discharge' if save_sim)
+        #: device tensors of the last run: 'scores' [N, n_obj_fns], 'gw' [N]
         self.results = None
 
-        # write out the observed discharge data used for the objective functions
+        # the observations the scores are computed against go next to the database (montecarlo.py:88)
         self.model.write_output_files(which='observed', parallel=self.p)
 
     def _set_sample(self, sample):
@@ -120,50 +72,6 @@ class MonteCarlo(object):
         # results; rows never leave their order here, so the map is built lazily on demand
         self.p_map = _LazyRowMap(self.sample_params)
         self.params = [(name, self.sample_params[:, k]) for k, name in enumerate(self.param_names)]
-
-    # ------------------------------------------------------------------ database
-    def _init_db(self):
-        n_samples = self.sample_params.shape[0]
-        if self.out_format == 'netcdf':
-            if not Dataset:
-                raise Exception(_NETCDF_OUT)
-            self.database = Dataset(self.db_file, 'w', format='NETCDF4', parallel=self.p)
-            self.database.description = "Monte Carlo Simulation outputs with SMARTpy v{}.".format(__version__)
-            self.database.createDimension('NbSamples', n_samples)
-            self.database.createDimension('NbParameters', len(self.model.parameters.names))
-            self.database.createDimension('NbObjFunctions', len(self.obj_fn_names))
-            params = self.database.createVariable('Parameters', np.float32, ('NbSamples', 'NbParameters'))
-            params.units = ', '.join(self.model.parameters.names)
-            objfns = self.database.createVariable('ObjFunctions', np.float32, ('NbSamples', 'NbObjFunctions'))
-            objfns.units = ', '.join(self.obj_fn_names)
-            if self.save_sim:
-                stamps = self.model.timeseries_report[1:]
-                self.database.createDimension('DateTime', len(stamps))
-                times = self.database.createVariable('DateTime', np.float64, ('DateTime',))
-                times.units = "seconds since 1970-01-01 00:00:00.0"
-                simu = self.database.createVariable('Simulations', np.float32, ('NbSamples', 'DateTime'))
-                simu.units = "Discharge in m3/s"
-                timestamps = (np.array(stamps, dtype='datetime64[s]') - np.datetime64('1970-01-01T00:00:00')) / \
-                    np.timedelta64(1, 's')
-                self.database.variables['DateTime'][0:len(stamps)] = timestamps
-        else:
-            self.database = open(self.db_file, 'w', newline='', encoding='utf8')
-            simu_steps = [dt.strftime('%Y-%m-%d %H:%M:%S') for dt in self.model.timeseries_report[1:]] \
-                if self.save_sim else []
-            self.database.write(','.join(self.obj_fn_names + self.param_names + simu_steps) + '\n')
-
-    def _save_block(self, first_row, obj_fns, parameters, simulations):
-        """Bulk form of save(): rows first_row .. first_row + n of the database."""
-        n = obj_fns.shape[0]
-        if self.out_format == 'netcdf':
-            self.database.variables['Parameters'][first_row:first_row + n, :] = parameters
-            self.database.variables['ObjFunctions'][first_row:first_row + n, :] = obj_fns
-            if self.save_sim:
-                self.database.variables['Simulations'][first_row:first_row + n, :] = simulations
-        else:
-            block = [obj_fns, parameters] + ([simulations] if self.save_sim else [])
-            table = np.concatenate(block, axis=1).astype(np.float32)   # '%.6e' of float32, montecarlo.py:226-231
-            np.savetxt(self.database, table, fmt='%.6e', delimiter=',')
 
     # ------------------------------------------------------------------ the spotpy protocol, kept for callers
     def parameters(self):
@@ -175,16 +83,11 @@ class MonteCarlo(object):
         return spotpy.parameter.generate([spotpy.parameter.List(name, column) for name, column in self.params])
 
     def simulation(self, vector):
-        discharge, groundwater_component = self.model.simulate(
-            {name: vector[k] for k, name in enumerate(self.param_names)})
-        return (
-            discharge, [groundwater_component]
-        )
+        discharge, groundwater_component = self.model.simulate(dict(zip(self.param_names, vector)))
+        return discharge, [groundwater_component]
 
     def evaluation(self):
-        return (
-            self.model.nd_flow, [self.constraints['gw']]
-        )
+        return self.model.nd_flow, [self.constraints['gw']]
 
     def objectivefunction(self, simulation, evaluation):
         """Scores of ONE simulated series, computed on the device by the same fused routine as
@@ -192,77 +95,75 @@ class MonteCarlo(object):
         from ..engine import score_series
         scores = score_series(np.asarray(simulation[0], dtype=np.float64), np.asarray(evaluation[0]))
         if self.constraints['gw']:
-            return scores + [groundwater_constraint(evaluation=evaluation[1], simulation=simulation[1])]
+            scores.append(groundwater_constraint(evaluation=evaluation[1], simulation=simulation[1]))
         return scores
 
     def save(self, obj_fns, parameters, simulations, *args, **kwargs):
-        parameters = np.asarray(parameters, dtype=np.float64)
-        index = self.p_map[tuple(parameters.tolist())] if self.out_format == 'netcdf' else 0
+        """One database row (the per-sample call of the reference, montecarlo.py:211-231)."""
+        if self.database is None:
+            self.database = self._new_database().open()
         sim = np.asarray(simulations[0], dtype=np.float64)[None, :] if self.save_sim else None
-        self._save_block(index, np.asarray(obj_fns, dtype=np.float64)[None, :], parameters[None, :], sim)
+        self.database.write_rows(np.asarray(obj_fns, dtype=np.float64)[None, :],
+                                 np.asarray(parameters, dtype=np.float64)[None, :], sim)
+
+    def _new_database(self):
+        stamps = self.model.timeseries_report[1:] if self.save_sim else ()
+        return SampleDatabase(self.db_file, self.out_format, self.obj_fn_names + self.param_names, stamps)
 
     # ------------------------------------------------------------------ run
     def run(self, compression=None):
-        """Run the simulations for the sample of parameter sets.
+        """Run the simulations for the sample of parameter sets and write the database.
 
-        compression: for 'csv' a bool (gzip the database); for 'netcdf' a bool or the zlib
-        complevel 1-9 (True = 6); None = no compression (montecarlo.py:132-177).
+        compression: True gzips the 'csv' database (montecarlo.py:132-177).
         """
+        import torch
         n_obj = len(self.obj_fn_names)
         rank, world = dist_utils.rank_world() if self.p else (0, 1)
-        writer = rank == 0          # with several ranks only the first one owns the database file
-        if writer:
-            self._init_db()
-        lo, hi = dist_utils.shard_bounds(self.sample_params.shape[0], rank, world)
+        if world > 1:
+            # ONE sample for the whole group: every rank built its own in its constructor (numpy's
+            # global generator is per process), rank 0's is the one that is run and written
+            self._set_sample(dist_utils.broadcast_rows(self.sample_params))
+        n_rows = self.sample_params.shape[0]
+        lo, hi = dist_utils.shard_bounds(n_rows, rank, world)
         engine = self.model.get_engine(report='summary', gw_constraint=self.constraints['gw'],
                                        precision=self.precision)
+        writer = rank == 0          # with several ranks only the first one owns the database file
+        if writer:
+            self.database = self._new_database().open()
         batch = _SAVE_SIM_BATCH if self.save_sim else max(hi - lo, 1)
-        scores_parts, gw_parts = [], []
+        blocks, series = [], []
         for first in range(lo, hi, batch):
             rows = self.sample_params[first:min(first + batch, hi)]
-            res = engine.run(rows, discharge=self.save_sim, scores=True, gw=True)
-            scores_parts.append(res['scores'])
-            gw_parts.append(res['gw'])
-            if self.save_sim and world == 1:
-                self._save_block(first, res['scores'][:, :n_obj].cpu().numpy(), rows,
-                                 res['discharge'].t().cpu().numpy())
-        import torch
-        scores = torch.cat(scores_parts) if scores_parts else torch.empty((0, 8), dtype=torch.float64)
-        gw = torch.cat(gw_parts) if gw_parts else torch.empty((0,), dtype=torch.float64)
+            block = torch.empty((rows.shape[0], 9), dtype=torch.float64, device=engine.device)
+            res = engine.run(rows, discharge=self.save_sim, scores=True, gw=True, out={'block': block})
+            blocks.append(block)
+            if self.save_sim:
+                sims = res['discharge'].t().contiguous()
+                if world == 1:
+                    self.database.write_rows(block[:, :n_obj].cpu().numpy(), rows, sims.cpu().numpy())
+                else:
+                    series.append(sims)
+        table = torch.cat(blocks) if blocks else torch.empty((0, 9), dtype=torch.float64, device=engine.device)
         if world > 1:
-            scores, gw = dist_utils.all_gather_rows(scores, gw, self.sample_params.shape[0])
-        self.results = {'scores': scores[:, :n_obj], 'gw': gw}
+            table = dist_utils.all_gather_rows(table, n_rows)
+        self.results = {'scores': table[:, :n_obj], 'gw': table[:, 8]}
+        if writer and not (self.save_sim and world == 1):
+            scores_host = table[:, :n_obj].cpu().numpy()
+        if world > 1 and self.save_sim:
+            # the simulated series of every shard travel to the writer rank by rank, in row order
+            mine = torch.cat(series) if series else torch.empty((0, engine.n_report), dtype=torch.float64,
+                                                                device=engine.device)
+            for r in range(world):
+                r_lo, r_hi = dist_utils.shard_bounds(n_rows, r, world)
+                sims = dist_utils.send_rows_to_first(mine, r, r_hi - r_lo)
+                if writer:
+                    self.database.write_rows(scores_host[r_lo:r_hi], self.sample_params[r_lo:r_hi], sims.cpu().numpy())
+        elif writer and not self.save_sim:
+            self.database.write_rows(scores_host, self.sample_params)
         if writer:
-            if not self.save_sim or world > 1:
-                self._save_block(0, scores[:, :n_obj].cpu().numpy(), self.sample_params, None)
-            self.database.close()
+            self.database.close(compression)
         if world > 1:
             dist_utils.barrier()
-        if not writer:
-            return
-
-        # if compression argument given, the file created will be compressed
-        if self.out_format == 'netcdf':
-            if compression is True:
-                compression = 6
-            if not isinstance(compression, bool) and isinstance(compression, (int, float)):
-                with Dataset(self.db_file, 'r') as src, Dataset(self.db_file.replace('.nc', '_.nc'), 'w') as dst:
-                    dst.description = src.description
-                    for name, dimension in src.dimensions.items():
-                        dst.createDimension(name, len(dimension))
-                    for name, variable in src.variables.items():
-                        v = dst.createVariable(name, variable.datatype, variable.dimensions,
-                                               zlib=True, complevel=compression)
-                        v.units = src.variables[name].units
-                        dst.variables[name][:] = src.variables[name][:]
-                remove(self.db_file)
-                rename(self.db_file.replace('.nc', '_.nc'), self.db_file)
-        elif self.out_format == 'csv':
-            if compression is True:
-                with open(self.db_file, 'rb') as f_in:
-                    with gzip.open(self.db_file + '.gz', 'wb') as f_out:
-                        shutil.copyfileobj(f_in, f_out)
-                remove(self.db_file)
 
     # ------------------------------------------------------------------ conditioning on the device
     def select_behavioural(self, conditioning):
@@ -283,24 +184,26 @@ class MonteCarlo(object):
         rows = best_rows(self.results['scores'], self.obj_fn_names, target, nb_best, constraining)
         return rows, self.sample_params[rows.cpu().numpy()]
 
+    def _sibling(self, source, func, parallel, save_sim, settings_filename):
+        """Set this (bare) instance up as a new experiment on the catchment of `source`, a run that is
+        still in memory -- what .from_run of Best / GLUE need before they pick their sample."""
+        MonteCarlo.__init__(self, source.catchment, source.root_f, source.in_format, source.out_format,
+                            parallel=source.parallel if parallel is None else parallel, save_sim=save_sim,
+                            func=func, settings_filename=settings_filename or source.settings_filename)
+        if source.results is None:
+            raise Exception("No results to condition: call run() on the sampling experiment first.")
+        if source.obj_fn_names != self.obj_fn_names and not set(self.obj_fn_names) <= set(source.obj_fn_names):
+            raise Exception("The sampling experiment does not hold the objective functions of this one.")
+
     # ------------------------------------------------------------------ reading a sample database back
     def _get_sampled_sets_from_file(self, file_location, param_names, obj_fn_names, decompression_csv):
         """-> (params float32 [N, 10], obj_fns float32 [N, k]) (montecarlo.py:233-262)."""
-        if self.out_format == 'netcdf':
-            if not Dataset:
-                raise Exception(_NETCDF_OUT)
-            with Dataset(file_location, 'r') as handle:
-                params = np.asarray(handle.variables['Parameters'][:, :])
-                obj_fns = np.asarray(handle.variables['ObjFunctions'][:, :])
-            return np.array(params, dtype=np.float32), np.array(obj_fns, dtype=np.float32)
-        opener = (lambda: gzip.open(file_location + '.gz', 'rt', encoding='utf8')) if decompression_csv else \
-            (lambda: open(file_location, 'r', encoding='utf8'))
-        obj_fns, params = list(), list()
-        with opener() as handle:
-            for row in DictReader(handle):
-                obj_fns.append([row[obj_fn] for obj_fn in obj_fn_names])
-                params.append([row[param] for param in param_names])
-        return np.array(params, dtype=np.float32), np.array(obj_fns, dtype=np.float32)
+        return read_sample_database(file_location, self.out_format, param_names, obj_fn_names,
+                                    gzipped=decompression_csv)
+
+    def _sampling_run_file(self):
+        """The database of the LHS run that Best / GLUE / Total condition or re-run."""
+        return database_path(self.model.out_f, self.catchment, 'lhs', self.out_format)
 
 
 class _LazyRowMap(object):

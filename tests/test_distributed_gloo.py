@@ -1,5 +1,7 @@
-"""CPU, world_size 2, gloo: the N > 1 host path -- row sharding and the one all-gather of the
-[rows, 8] score block + gw that follows the kernel (smartpy_b200/distributed.py)."""
+"""CPU, world_size 2, gloo: the N > 1 host path -- row sharding, the one all-gather of the
+[rows, 9] block (8 scores + gw) that follows the kernel, the broadcast that gives every rank of a
+sharded Monte Carlo run the SAME sample, and the hand-over of simulated series to the rank that
+writes the database (smartpy_b200/distributed.py)."""
 import os
 import socket
 
@@ -24,11 +26,33 @@ def _worker(rank, world, port, n_rows, out_dir):
     lo, hi = du.shard_bounds(n_rows, rank, world)
     # each rank "computes" its shard: score[row, k] = row + k / 10, gw[row] = -row
     rows = torch.arange(lo, hi, dtype=torch.float64)
-    scores = rows[:, None] + torch.arange(8, dtype=torch.float64)[None, :] / 10
-    gw = -rows
-    full_scores, full_gw = du.all_gather_rows(scores, gw, n_rows)
-    np.save(os.path.join(out_dir, "scores_%d.npy" % rank), full_scores.numpy())
-    np.save(os.path.join(out_dir, "gw_%d.npy" % rank), full_gw.numpy())
+    block = torch.empty((hi - lo, 9), dtype=torch.float64)
+    block[:, :8] = rows[:, None] + torch.arange(8, dtype=torch.float64)[None, :] / 10
+    block[:, 8] = -rows
+    full = du.all_gather_rows(block, n_rows)
+    assert full.shape == (n_rows, 9)
+    np.save(os.path.join(out_dir, "scores_%d.npy" % rank), full[:, :8].numpy())
+    np.save(os.path.join(out_dir, "gw_%d.npy" % rank), full[:, 8].numpy())
+    # every rank draws its OWN sample (unseeded generator); after the broadcast all hold rank 0's
+    mine = np.random.RandomState(1000 + rank).rand(n_rows, 10)
+    same = du.broadcast_rows(mine)
+    np.save(os.path.join(out_dir, "sample_%d.npy" % rank), same)
+    assert (rank == 0) == np.array_equal(same, mine)
+    # simulated series travel to the writer rank shard by shard, in row order
+    sims = rows[:, None] * torch.ones((1, 5), dtype=torch.float64)
+    got = []
+    for r in range(world):
+        r_lo, r_hi = du.shard_bounds(n_rows, r, world)
+        part = du.send_rows_to_first(sims, r, r_hi - r_lo)
+        assert (part is not None) == (rank == 0)
+        if rank == 0:
+            got.append(part)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "sims.npy"), torch.cat(got).numpy())
+    # an empty shard (more ranks than rows) must not break the collective
+    lo1, hi1 = du.shard_bounds(1, rank, world)
+    tiny = du.all_gather_rows(torch.full((hi1 - lo1, 9), 7.0, dtype=torch.float64), 1)
+    assert tiny.shape == (1, 9) and bool((tiny == 7.0).all())
     dist.destroy_process_group()
 
 
@@ -40,6 +64,10 @@ def test_shard_and_all_gather_world2(tmp_path):
         for rank in range(2):
             assert np.array_equal(np.load(tmp_path / ("scores_%d.npy" % rank)), expect)
             assert np.array_equal(np.load(tmp_path / ("gw_%d.npy" % rank)), -np.arange(n_rows, dtype=np.float64))
+            assert np.array_equal(np.load(tmp_path / ("sample_%d.npy" % rank)),
+                                  np.random.RandomState(1000).rand(n_rows, 10))
+        assert np.array_equal(np.load(tmp_path / "sims.npy"),
+                              np.arange(n_rows, dtype=np.float64)[:, None] * np.ones((1, 5)))
 
 
 def _best_worker(rank, world, port, out_dir):

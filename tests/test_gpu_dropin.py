@@ -112,3 +112,44 @@ def test_run_mc_lhs(catchment_dir):  # noqa: F811
     total.model.extra = dict(EXTRA)          # as in the reference, `extra` is set on each new setup
     total.run()
     assert np.allclose(total.results['scores'][:, 0].cpu().numpy(), sc_ref[:, 0], atol=1e-4)
+
+
+def test_best_and_glue_from_a_run_in_memory(catchment_dir):  # noqa: F811
+    """Best.from_run / GLUE.from_run / Total.from_run: the score table a sampling run left on the
+    device is conditioned there (smart_best_rows / smart_condition_rows) and the selected rows go
+    back through the same engine -- no database round trip, binary64 parameters."""
+    from smartpy_b200 import montecarlo
+    np.random.seed(7)
+    lhs = montecarlo.LHS('Catchment', catchment_dir, 'csv', 'csv', sample_size=60)
+    lhs.model.extra = dict(EXTRA)
+    with pytest.raises(Exception, match="call run"):
+        montecarlo.Best.from_run(lhs, 'NSE', 3)
+    lhs.run()
+    sc = lhs.results['scores'].cpu().numpy()
+    # Best: constraint + top-k, ascending with the best last, exact float64 rows of the sample
+    kge_floor = float(np.median(sc[:, 1]))
+    best = montecarlo.Best.from_run(lhs, target='NSE', nb_best=5, constraining={'KGE': ('min', (kge_floor,))})
+    kept = np.nonzero(sc[:, 1] >= kge_floor)[0]
+    expect = kept[np.argsort(sc[kept, 0], kind='stable')][-5:]
+    assert best.best_rows.tolist() == expect.tolist()
+    assert np.array_equal(best.best_params, lhs.sample_params[expect])
+    assert best.db_file.endswith('Catchment.SMART.5best') and best.target_fn_index == [0]
+    assert best.constraints_indices == [1] and best.constraints_types == ['min']
+    best.model.extra = dict(EXTRA)
+    best.run()
+    again = best.results['scores'].cpu().numpy()
+    assert np.array_equal(again, sc[expect], equal_nan=True)        # same period, same parameters: same bits
+    with open(best.db_file) as f:
+        assert len(f.read().splitlines()) == 6
+    with pytest.raises(Exception, match="restrained sample size"):
+        montecarlo.Best.from_run(lhs, 'NSE', 40, constraining={'KGE': ('min', (kge_floor,))})
+    with pytest.raises(Exception, match="not recognised"):
+        montecarlo.Best.from_run(lhs, 'nse', 2)
+    # GLUE: behavioural rows in sample order
+    glue = montecarlo.GLUE.from_run(lhs, {'NSE': ('min', (float(np.median(sc[:, 0])),)), 'PBias': ('inside', (-90.0, 90.0))})
+    mask = (sc[:, 0] >= np.median(sc[:, 0])) & (sc[:, 5] >= -90.0) & (sc[:, 5] <= 90.0)
+    assert glue.behavioural_rows.tolist() == np.nonzero(mask)[0].tolist()
+    assert np.array_equal(glue.behavioural_params, lhs.sample_params[mask])
+    # Total: the whole sample again
+    total = montecarlo.Total.from_run(lhs)
+    assert np.array_equal(total.sample_params, lhs.sample_params) and total.db_file.endswith('.SMART.total')

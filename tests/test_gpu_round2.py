@@ -279,7 +279,7 @@ def test_wild_members_run_in_their_own_ctas_and_change_no_bit(catchment, oracle_
 def test_scores_and_gw_written_into_a_gather_block(catchment):
     import torch
     g = load_golden("runs_members")
-    eng = make_engine(catchment, n_steps=24 * 300)
+    eng = make_engine(catchment, n_steps=24 * 300, warm_up_days=30)
     ref = eng.run(g["params"], scores=True, gw=True)
     blk = torch.full((len(g["params"]), 9), -7.0, dtype=torch.float64, device=ref["gw"].device)
     res = eng.run(g["params"], scores=True, gw=True, out={"block": blk})
@@ -292,9 +292,9 @@ def test_scores_and_gw_written_into_a_gather_block(catchment):
 
 def test_run_host_round_trip_reuses_its_staging(catchment):
     g = load_golden("runs_members")
-    eng = make_engine(catchment, n_steps=24 * 300)
+    eng = make_engine(catchment, n_steps=24 * 300, warm_up_days=30)
     dev = eng.run(g["params"], scores=True, gw=True)
-    out = eng.run_host(g["params"])
+    out = eng.run_host(g["params"], copy=True)
     assert isinstance(out["scores"], np.ndarray) and out["scores"].shape == (len(g["params"]), 8)
     assert np.array_equal(out["scores"], dev["scores"].cpu().numpy(), equal_nan=True)
     assert np.array_equal(out["gw"], dev["gw"].cpu().numpy())
@@ -302,6 +302,8 @@ def test_run_host_round_trip_reuses_its_staging(catchment):
     again = eng.run_host(g["params"][::-1].copy())
     assert {k: v.data_ptr() for k, v in eng._staging.items()} == staging     # no new pinned or device buffers
     assert np.array_equal(again["scores"][::-1], out["scores"], equal_nan=True)
+    view = eng.run_host(g["params"])["scores"]                                # default: a view of the staging buffer,
+    assert not view.flags.owndata and np.array_equal(view, out["scores"], equal_nan=True)   # valid until the next call
     # the C entry point with host pointers: a second call of the same size allocates nothing new
     import ctypes
     from smartpy_b200 import _native

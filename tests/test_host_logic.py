@@ -356,3 +356,59 @@ def test_device_conditioning_argument_checks():
         conditioning.behavioural_rows(t, names, {'NSE': ('about', (0.3,))})
     with pytest.raises(RuntimeError, match="no CPU path"):
         conditioning.behavioural_rows(t, names, {'NSE': ('min', (0.1,))})
+
+
+def test_sample_database_round_trip(tmp_path):
+    """database.SampleDatabase writes the reference's format ('%.6e' of the float32 value, header =
+    objective functions + parameters + report stamps, optional gzip) in bulk; read_sample_database
+    finds the columns by name and returns float32 -- checked against a row-by-row restatement of
+    the reference's writer (montecarlo.py:226-231) and reader (:247-262)."""
+    import gzip
+    from csv import DictReader
+    from datetime import datetime, timedelta
+    from smartpy_b200.montecarlo.database import SampleDatabase, read_sample_database, database_path
+    rng = np.random.RandomState(0)
+    fns, names = ['NSE', 'KGE', 'GW'], ['T', 'C', 'H']
+    scores, params, sims = rng.randn(7, 3) * 10, rng.rand(7, 3) * 100, rng.rand(7, 4) * 1e-3
+    stamps = [datetime(2007, 1, 1, 9) + k * timedelta(days=1) for k in range(4)]
+    path = database_path(str(tmp_path) + os.sep, 'Catchment', 'lhs', 'csv')
+    assert path.endswith('Catchment.SMART.lhs') and database_path('x/', 'C', 'glue', 'netcdf') == 'x/C.SMART.glue.nc'
+    db = SampleDatabase(path, 'csv', fns + names, stamps).open()
+    db.write_rows(scores[:3], params[:3], sims[:3])
+    db.write_rows(scores[3:], params[3:], sims[3:])
+    with pytest.raises(ValueError):
+        db.write_rows(scores, params)                                 # the series are part of every row
+    db.close()
+    lines = open(path).read().splitlines()
+    assert lines[0] == 'NSE,KGE,GW,T,C,H,2007-01-01 09:00:00,2007-01-02 09:00:00,2007-01-03 09:00:00,2007-01-04 09:00:00'
+    for r in range(7):                                                # the reference's per-row formatting
+        values = np.concatenate([scores[r], params[r], sims[r]])
+        assert lines[1 + r] == ','.join('%.6e' % np.float32(v) for v in values)
+    p, f = read_sample_database(path, 'csv', ['H', 'T'], ['GW', 'NSE'])
+    rows = list(DictReader(open(path)))
+    assert np.array_equal(p, np.array([[row['H'], row['T']] for row in rows], dtype=np.float32))
+    assert np.array_equal(f, np.array([[row['GW'], row['NSE']] for row in rows], dtype=np.float32))
+    # gzip: <file>.gz replaces the file
+    db = SampleDatabase(path, 'csv', fns + names).open()
+    db.write_rows(scores, params)
+    db.close(compression=True)
+    assert not os.path.exists(path) and gzip.open(path + '.gz', 'rt').readline().strip() == 'NSE,KGE,GW,T,C,H'
+    p2, _ = read_sample_database(path, 'csv', names, fns, gzipped=True)
+    assert np.array_equal(p2, np.array([['%.6e' % np.float32(v) for v in row] for row in params], dtype=np.float32))
+    with pytest.raises(Exception, match="netCDF4"):
+        SampleDatabase(path, 'netcdf', fns + names)
+    with pytest.raises(Exception, match="netCDF4"):
+        read_sample_database(path, 'netcdf', names, fns)
+
+
+def test_no_netcdf_code_is_left_unexecuted():
+    """'netcdf' takes the reference's "package netCDF4 missing" exit everywhere (inout.py, database.py);
+    nothing imports netCDF4."""
+    import smartpy_b200.inout as inout
+    from smartpy_b200.montecarlo import database, montecarlo
+    for module in (inout, database, montecarlo):
+        assert 'Dataset' not in vars(module)
+    with pytest.raises(Exception, match="netCDF4"):
+        inout.read_rain_file('nowhere.nc', 'netcdf')
+    with pytest.raises(Exception, match="netCDF4"):
+        inout.write_flow_file_from_nds([], [], 'nowhere', 'netcdf')

@@ -128,3 +128,24 @@ def test_conditioning_matches_reference(ref):
     a = Best._get_best_sets(params, fns[:, 1:], [(0.5,), (-1.0,)], ['max', 'min'], fns[:, :1], 9)
     b = ref.best.Best._get_best_sets(params, fns[:, 1:], [(0.5,), (-1.0,)], ['max', 'min'], fns[:, :1], 9)
     assert np.array_equal(a, b)
+
+
+def test_sample_database_reader_matches_the_reference_algorithm_on_its_example_file():
+    """read_sample_database against the reference's reader restated here (csv.DictReader row by row,
+    strings to np.float32 arrays, montecarlo.py:247-262) on the reference's own example database
+    (written by an older version: six extra columns, found by name)."""
+    from csv import DictReader
+    from smartpy_b200.montecarlo.database import read_sample_database
+    from smartpy_b200.parameters import Parameters
+    path = os.path.join(REFERENCE, "examples", "out", "ExampleDaily", "ExampleDaily.SMART.lhs")
+    names = Parameters().names
+    fns = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
+    params, obj_fns = read_sample_database(path, 'csv', names, fns)
+    with open(path, 'r', encoding='utf8') as handle:
+        rows = list(DictReader(handle))
+    ref_params = np.array([[row[p] for p in names] for row in rows], dtype=np.float32)
+    ref_fns = np.array([[row[f] for f in fns] for row in rows], dtype=np.float32)
+    assert params.dtype == np.float32 and obj_fns.dtype == np.float32
+    assert np.array_equal(params, ref_params) and np.array_equal(obj_fns, ref_fns)
+    with pytest.raises(KeyError):
+        read_sample_database(path, 'csv', names, ['NoSuchScore'])

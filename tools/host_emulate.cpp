@@ -22,17 +22,17 @@ using namespace smart;
 // mode 0: general, 1: fast (first form), 2: fast per-step, 3: block mode (one report per block of
 // `gap` steps), 4: block-sub mode (blocks of `rep` steps, reports every `gap` steps inside them).
 // Mirrors run_member/run_timeline of smart_kernels.cu for one member, summary or raw reporting.
+template <typename R>
 static int emulate(int mode, int rep, double area, double dt, long T, long W, const double *rain,
                    const double *peva, const double *par, int has_extra, double aar_ro,
                    const double *split, int report_type, int gap, double *discharge, double *gw_out)
 {
-    typedef double R;
     const double Tt = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
     const double SK = par[6], FK = par[7], GK = par[8], RK = par[9];
     MemberPar<R> p;
     p.Td = Tt; p.C = C; p.D = D; p.omD = 1.0 - D; p.Hz = H / Z; p.Sz = S / Z; p.z = Z / 6.0;
     p.r_sk = dt / (SK * 3600.0); p.r_fk = dt / (FK * 3600.0); p.r_gk = dt / (GK * 3600.0); p.r_rk = dt / (RK * 3600.0);
-    R kc[7] = {C, D, 1.0 - D, p.r_sk, p.r_fk, p.r_gk, p.r_rk};
+    R kc[7] = {R(C), R(D), R(1.0 - D), p.r_sk, p.r_fk, p.r_gk, p.r_rk};
     double kb[7];
     {
         const double cx[3] = {1.0 - p.r_sk, 1.0 - p.r_fk, 1.0 - p.r_gk}, rx[3] = {p.r_sk, p.r_fk, p.r_gk};
@@ -135,8 +135,18 @@ extern "C" int emulate_run(int mode, double area, double dt, long T, long W, con
                            const double *peva, const double *par, int has_extra, double aar_ro,
                            const double *split, int report_type, int gap, double *discharge, double *gw_out)
 {
-    return emulate(mode, gap, area, dt, T, W, rain, peva, par, has_extra, aar_ro, split, report_type, gap, discharge,
-                   gw_out);
+    return emulate<double>(mode, gap, area, dt, T, W, rain, peva, par, has_extra, aar_ro, split, report_type, gap,
+                           discharge, gw_out);
+}
+
+// binary32 state (the FP32 mode of the kernels; the GPU unit may contract a * b + c where this
+// build does not, so this reproduces the size of the FP32 error, not its bits)
+extern "C" int emulate_run_f32(int mode, double area, double dt, long T, long W, const double *rain,
+                               const double *peva, const double *par, int has_extra, double aar_ro,
+                               const double *split, int report_type, int gap, double *discharge, double *gw_out)
+{
+    return emulate<float>(mode, gap, area, dt, T, W, rain, peva, par, has_extra, aar_ro, split, report_type, gap,
+                          discharge, gw_out);
 }
 
 // block-sub mode: forcing constant inside aligned blocks of `rep` steps, reports every `gap` steps
@@ -144,5 +154,6 @@ extern "C" int emulate_run_sub(int rep, double area, double dt, long T, long W, 
                                const double *peva, const double *par, int has_extra, double aar_ro,
                                const double *split, int report_type, int gap, double *discharge, double *gw_out)
 {
-    return emulate(4, rep, area, dt, T, W, rain, peva, par, has_extra, aar_ro, split, report_type, gap, discharge, gw_out);
+    return emulate<double>(4, rep, area, dt, T, W, rain, peva, par, has_extra, aar_ro, split, report_type, gap, discharge,
+                           gw_out);
 }
