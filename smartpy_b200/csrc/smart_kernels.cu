@@ -145,6 +145,7 @@ struct KArgs {
     long long n_threads;         // threads of the launch that may carry a member (N, or the length of order)
     long long N, T, W, ld_q, ld_s, ld_g;
     int C, mpc, gap, report_type;
+    int tpc, pad1;               // threads per catchment (multi-catchment): mpc, or mpc padded to whole warps
     int chunk, kc, use_tma, force_general;
     int has_extra, best_col, best_sign, first_report;
     int skew, skew_groups;       // start delay of a CTA in cycles per group step, number of groups (0 = none)
@@ -465,7 +466,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                         const R ex = static_cast<R>(ex_d);
                         const R hex = fp_.Hz * ex;
                         const unsigned mask = __activemask();
-                        if (kWide && !carry.valid) {
+                        if (!carry.valid) {
                             carry.tot = soil_total(s);
                             carry.valid = true;
                         }
@@ -477,7 +478,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                             after_hour(q_riv, q_gw, q_in);
                         }
                     } else {
-                        dry_block_soil<R>(s, kconst[0], ex_d, rep);
+                        dry_block_soil<R>(s, kconst[0], fp_.z, ex_d, rep);
                         carry.valid = false;
 #pragma unroll 2
                         for (int h = 0; h < rep; ++h) {
@@ -723,6 +724,10 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         s.ove = s.ove + s.dra;
         s.sgw = s.sgw + s.dgw;
         s.dra = s.dgw = R(0);
+        if (sizeof(R) == 4) {   // binary32 fast form: the soil as deficits z - level (fast_wet_soil_deficit)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(static_cast<double>(p.z) - v[5 + k] * to_mm);
+        }
     }
 
     double gw = 0.0;
@@ -772,6 +777,16 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
     const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + tid;
     bool active = m_raw < a.n_threads;
     long long m = active ? m_raw : a.n_threads - 1;   // tail threads shadow the last one, store nothing
+    int c = 0;
+    if (!kSingle) {
+        // thread -> (catchment, member of it).  a.tpc threads serve one catchment: a.mpc of them carry
+        // a member, the others (padding up to whole warps, see tpc_of) shadow its last member, so
+        // that no warp mixes the weather of two catchments.
+        c = static_cast<int>(m / a.tpc);
+        const int l = static_cast<int>(m - static_cast<long long>(c) * a.tpc);
+        active = active && l < a.mpc;
+        m = static_cast<long long>(c) * a.mpc + (l < a.mpc ? l : a.mpc - 1);
+    }
     if (a.order != nullptr) {
         // (single catchment, no [t][member] output: validate().)  Idle slots hold -1; an idle thread
         // shadows the member of its CTA's first thread, a CTA whose first slot is idle has no member.
@@ -809,9 +824,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         if ((need_general != 0) != (kVariant == kVariantGeneral)) return;   // the other launch owns this CTA
     }
 
-    constexpr bool multi = !kSingle;
-    const int c = multi ? static_cast<int>(m / a.mpc) : 0;
-    const int c_base = multi ? static_cast<int>((static_cast<long long>(blockIdx.x) * BLOCK) / a.mpc) : 0;
+    const int c_base = kSingle ? 0 : static_cast<int>((static_cast<long long>(blockIdx.x) * BLOCK) / a.tpc);
     const int col = c - c_base;
     const double area = a.area[c];
 
@@ -981,6 +994,22 @@ int64_t n_report_of(const smart_batch_desc *d)
 
 constexpr int kBlockSmall = 64, kBlockLarge = 128;
 
+// Threads that serve one catchment of a multi-catchment batch.  A warp that holds members of two
+// catchments walks two weathers: on most days one is wet and the other dry, the warp pays for
+// both paths, and the other warps of its CTA wait for it at the staging barrier (C4a measured at
+// twice the cost per member-step of a uniform batch).  When it costs < 50 % more threads, every
+// catchment gets whole warps of its own: members_per_catchment rounded up to a multiple of 32,
+// the extra lanes idle (they shadow the catchment's last member and store nothing).
+int tpc_of(const smart_batch_desc *d)
+{
+    if (d->n_catchments <= 1) return 1;
+    const int mpc = d->members_per_catchment;
+    const int padded = (mpc + 31) / 32 * 32;
+    static const bool off = getenv("SMART_B200_NO_WARP_PADDING") != nullptr;
+    return (!off && 2 * padded <= 3 * mpc) ? padded : mpc;
+}
+
+
 // Members per CTA.  Members cost the same, so a launch finishes when the SM with the most
 // members does: 64-thread CTAs spread a batch of a few waves more evenly over the 148 SMs
 // (config C2: 1e5 members = 675.7 per SM); 128-thread CTAs halve the per-CTA staging for
@@ -992,12 +1021,19 @@ int block_of(const smart_batch_desc *d)
         return e ? atoi(e) : 0;
     }();
     if (forced == kBlockSmall || forced == kBlockLarge) return forced;
+    if (d->n_catchments > 1 && tpc_of(d) != d->members_per_catchment) {
+        // padded catchments: a CTA that holds whole catchments (or part of one) has one pace
+        if (tpc_of(d) % kBlockLarge == 0) return kBlockLarge;
+        if (tpc_of(d) % kBlockSmall == 0 || kBlockSmall % tpc_of(d) == 0) return kBlockSmall;
+    }
     return d->n_members <= 148LL * 736 * 8 ? kBlockSmall : kBlockLarge;
 }
 
-// threads of a launch that may carry a member: one per member, or one per slot of member_order
+// threads of a launch that may carry a member: one per member, one per slot of member_order, or
+// tpc_of() per catchment
 int64_t n_threads_of(const smart_batch_desc *d)
 {
+    if (d->n_catchments > 1) return static_cast<int64_t>(d->n_catchments) * tpc_of(d);
     return d->member_order && d->member_order_len > 0 ? d->member_order_len : d->n_members;
 }
 
@@ -1090,6 +1126,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     a.ld_q = d->ld_discharge;
     a.C = d->n_catchments;
     a.mpc = d->n_catchments > 1 ? d->members_per_catchment : 1;
+    a.tpc = d->n_catchments > 1 ? tpc_of(d) : 1;
     a.gap = d->report_gap;
     a.report_type = d->report_type;
     a.has_extra = d->has_extra;
@@ -1124,7 +1161,8 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
                              (reinterpret_cast<uintptr_t>(d->peva) % 16 == 0);
         a.use_tma = (aligned && !(d->flags & SMART_FLAG_NO_TMA)) ? 1 : 0;
     } else {
-        a.kc = (block - 1) / a.mpc + 2;              // catchments one CTA can straddle
+        a.kc = (block % a.tpc == 0 || a.tpc % block == 0) ? (block + a.tpc - 1) / a.tpc   // CTAs aligned with catchments
+                                                          : (block - 1) / a.tpc + 2;      // catchments one CTA can straddle
         if (a.kc > a.C) a.kc = a.C;
         int chunk = (12 * 1024) / (2 * 2 * 8 * a.kc);   // 12 KB of forcing stages per CTA
         chunk = chunk > (daily ? 64 : 512) ? (daily ? 64 : 512) : chunk;

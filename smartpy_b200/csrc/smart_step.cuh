@@ -277,17 +277,91 @@ __device__ __forceinline__ R soil_total(const MemberState<R> &s)
 // the scoreboard does not look at predicates -- in every wet hour of every member.
 // mask: the lanes of the warp that are in this call together (__activemask() taken by the caller
 // where it is known to be stable, e.g. once per wet block).
+// ---- binary32 state: the soil as DEFICITS ----------------------------------------------------
+// In binary32 the six soil values hold d = z - level, how far each layer is from full, not the
+// level.  Why: a wet column sits at or near capacity (18 mm per layer for Z = 109), the hourly
+// leaks are 1e-3 mm, and level - leak rounds to the level's ulp (2e-6 mm): the water the soil
+// actually gives up each hour differs from the leak by up to 5e-4 of it, and under constant forcing
+// in a saturated column it is the SAME rounding every hour -- a bias, not noise (measured on an
+// LHS sample of 1e5 members: |dNSE| up to 2.3e-5 against the binary64 kernel, 157 members above the
+// 1e-5 bar; profiles/r02_fp32_*.json).  The deficit of a wet column is itself of the size of the
+// leaks, so binary32 resolves it to 1e-10 mm; in a dry column the deficit is large and coarse
+// (2e-6 mm) but so is every flux that touches it.  Water balance then holds to 1e-7 relative in
+// both regimes, with the same number of operations: the fill ladder needs ONE addition per layer
+// (t = d - water: the layer takes everything iff t >= 0), the three leak passes nine per layer
+// as before.  carry.tot holds the SUM OF DEFICITS (soil total = 6 z - that).
+template <int kStride, bool kTotKnown>
+__device__ __forceinline__ void fast_wet_soil_deficit(MemberState<float> &s, const FastPar<float> &p, float D, float omD,
+                                                      FastCarry<float> &carry, float ex, float hex, unsigned mask,
+                                                      float &in_quick, float &in_int, float &in_gw)
+{
+    float sd = carry.tot;
+    if (!kTotKnown) {
+        if (__any_sync(mask, !carry.valid)) {
+            if (!carry.valid) sd = soil_total(s);
+        }
+    }
+    const float tot = fma(6.0f, p.z, -sd);          // structure.py:350
+    in_quick = hex * tot;                           // :363-364
+    const float u0 = fma(hex, tot, -ex);            // u = -(excess rain still to place) <= 0
+    float u = u0;
+    auto fill = [&](int i) {                        // :367-374: room = the deficit itself
+        const float t = s.ly[i] + u;
+        const bool fits = sign_clear(t);
+        s.ly[i] = fits ? t : 0.0f;
+        u = fits ? 0.0f : t;
+        return fits;
+    };
+#ifndef SMART_NO_EARLY_OUT
+    const bool done = fill(0);
+    if (__any_sync(mask, !done)) {
+        fill(1); fill(2); fill(3); fill(4); fill(5);
+    }
+#else
+    fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
+#endif
+    in_quick = fma(D, -u, in_quick);                // + D * saturation excess (:376)
+    const float sp = p.Sz * tot;                    // :379
+    float pw[6];
+    pw[0] = sp;
+    pw[1] = sp * sp;
+    pw[2] = pw[1] * sp;
+    pw[3] = pw[1] * pw[1];
+    pw[4] = pw[3] * sp;
+    pw[5] = pw[2] * pw[2];
+    // the three passes act on the LEVEL z - d of each layer (:381-399); what they take out together
+    // is added to the deficit, and the same numbers -- no second rounding -- go to the stores
+    float leak_int = 0.0f, leak_all = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float f2 = i == 0 ? sp : sp * inv_const<float>(i);
+        const float l0 = p.z - s.ly[i];
+        const float l1 = fma(-l0, pw[i], l0);                       // after the interflow pass
+        const float l2 = fma(-l1, f2, l1);                          // after the shallow groundwater pass
+        leak_int = fma(l0, pw[i], leak_int);
+        const float out = fma(l2, pw[5 - i], fma(l1, f2, l0 * pw[i]));   // all three passes
+        s.ly[i] += out;
+        leak_all += out;
+    }
+    in_int = fma(omD, -u, leak_int);                // (1 - D) * saturation excess + interflow (:377, :381-385)
+    in_gw = leak_all - leak_int;
+    // sum of deficits after this hour: minus what the fill placed (u - u0 >= 0), plus the leaks
+    carry.tot = ((sd + u0) - u) + leak_all;
+    carry.valid = true;
+}
+
 template <typename R, int kStride, bool kTotKnown = false>
 __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R> &p, R D, R omD,
                                               FastCarry<R> &carry, R ex, R hex, unsigned mask, R &in_quick, R &in_int,
                                               R &in_gw)
 {
-    constexpr bool kLeakByDifference = sizeof(R) == 8;
+    if constexpr (sizeof(R) == 4) {
+        fast_wet_soil_deficit<kStride, kTotKnown>(s, p, D, omD, carry, ex, hex, mask, in_quick, in_int, in_gw);
+        return;
+    }
     const R zero = R(0);
     R tot = carry.tot;
-    if (!kLeakByDifference) {
-        tot = soil_total(s);                        // binary32 state never carries the total
-    } else if (!kTotKnown) {
+    if (!kTotKnown) {
         if (__any_sync(mask, !carry.valid)) {
             if (!carry.valid) tot = soil_total(s);
         }
@@ -322,7 +396,7 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
     pw[3] = pw[1] * pw[1];
     pw[4] = pw[3] * sp;
     pw[5] = pw[2] * pw[2];
-    if (kLeakByDifference) {
+    {
         // soil total after the fill, summed like tot1/tot3 so that a zero leak gives exactly 0
         const R tot_f = soil_total(s);
 #pragma unroll
@@ -340,49 +414,29 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
         in_gw = tot1 - tot3;
         carry.tot = tot3;
         carry.valid = true;
-    } else {
-        // binary32 state: what a pass takes out of a layer is read back as the difference of the
-        // layer before and after (exact: the two values are within a factor of two), so that the
-        // water handed to the stores is EXACTLY the water the soil lost.  Forming the leak, adding it
-        // to the inflow and subtracting it from the layer rounds the subtraction to the layer's ulp
-        // (2e-6 mm for an 18 mm layer, against leaks of 1e-3 mm per hour), and in a saturated column
-        // under constant forcing that rounding is the same every hour: a mass-balance bias of up to
-        // 5e-4 of the leak, |dNSE| up to 2.3e-5 over an LHS sample (profiles/r02_fp32_*.json).
-        in_gw = zero;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const R nl = fma(-s.ly[i], pw[i], s.ly[i]);
-            in_int += s.ly[i] - nl;
-            s.ly[i] = nl;
-        }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const R nl = fma(-s.ly[i], i == 0 ? sp : sp * inv_const<R>(i), s.ly[i]);
-            in_gw += s.ly[i] - nl;
-            s.ly[i] = nl;
-        }
-#pragma unroll
-        for (int i = 5; i >= 0; --i) {
-            const R nl = fma(-s.ly[i], pw[5 - i], s.ly[i]);
-            in_gw += s.ly[i] - nl;
-            s.ly[i] = nl;
-        }
-        carry.valid = false;
     }
 }
 
 // Dry hour, soil part (structure.py:407-419): the deficit d = peva - rain * T > 0 is taken from
 // the layers top down, decayed by C each time a layer runs empty.
 template <typename R>
-__device__ __forceinline__ void fast_dry_soil(MemberState<R> &s, R C, R d)
+__device__ __forceinline__ void fast_dry_soil(MemberState<R> &s, R C, R d, R z)
 {
     const R zero = R(0);
     auto take = [&](int i) {
-        const R t = s.ly[i] - d;
-        const bool enough = sign_clear(t);          // level >= deficit
-        s.ly[i] = enough ? t : zero;
-        d = enough ? zero : C * (-t);
-        return enough;
+        if constexpr (sizeof(R) == 8) {
+            const R t = s.ly[i] - d;
+            const bool enough = sign_clear(t);      // level >= deficit
+            s.ly[i] = enough ? t : zero;
+            d = enough ? zero : C * (-t);
+            return enough;
+        } else {                                    // binary32: s.ly holds z - level (see fast_wet_soil_deficit)
+            const R t = (z - s.ly[i]) - d;
+            const bool enough = sign_clear(t);
+            s.ly[i] = enough ? s.ly[i] + d : z;
+            d = enough ? zero : C * (-t);
+            return enough;
+        }
     };
 #ifndef SMART_NO_EARLY_OUT
     const bool done = take(0);
@@ -422,7 +476,7 @@ __device__ __forceinline__ void smart_step_fast(MemberState<R> &s, const FastPar
         fast_wet_soil<R, kStride>(s, p, kc[1 * kStride], kc[2 * kStride], carry, ex, p.Hz * ex, __activemask(), in_quick,
                                   in_int, in_gw);
     } else {
-        fast_dry_soil<R>(s, kc[0], static_cast<R>(-ex_d));
+        fast_dry_soil<R>(s, kc[0], static_cast<R>(-ex_d), p.z);
         carry.valid = false;
     }
 
@@ -463,14 +517,16 @@ constexpr int kWetUnroll = SMART_WET_UNROLL;   // unroll factor of the wet-block
 // demand) whole steps in one multiplication, then one ordinary ladder step (from k down) empties
 // it and the demand decays by C again.  Always binary64 arithmetic, whatever R is.
 template <typename R>
-__device__ __forceinline__ void dry_block_soil(MemberState<R> &s, R Cpar, double ex_d, int rep)
+__device__ __forceinline__ void dry_block_soil(MemberState<R> &s, R Cpar, R zpar, double ex_d, int rep)
 {
+    constexpr bool kDeficits = sizeof(R) == 4;   // binary32 state keeps z - level (fast_wet_soil_deficit)
+    const double z = static_cast<double>(zpar);
     double left = static_cast<double>(rep);      // steps of the block still to account for
     double dem = -ex_d;                          // demand arriving at layer k in each of them
     const double C = static_cast<double>(Cpar);
     double ly[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) ly[k] = static_cast<double>(s.ly[k]);
+    for (int k = 0; k < 6; ++k) ly[k] = kDeficits ? z - static_cast<double>(s.ly[k]) : static_cast<double>(s.ly[k]);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         if (__any_sync(__activemask(), left > 0.0)) {
@@ -516,17 +572,17 @@ __device__ __forceinline__ void dry_block_soil(MemberState<R> &s, R Cpar, double
     }
     // (after layer 5 nothing is left to take: remaining steps of the block change nothing)
 #pragma unroll
-    for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(ly[k]);
+    for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(kDeficits ? z - ly[k] : ly[k]);
 }
 
 // Dry block with one report at its end: soil as above, stores + river + the two running sums by
 // the linear recurrences.  acc += sum of river outflow over the block, agw += sum of groundwater
 // outflow (mm).
 template <typename R, int kStride>
-__device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, const double *kb, double ex_d, int rep,
-                                               R &acc, R &agw)
+__device__ __forceinline__ void dry_block_fast(MemberState<R> &s, const R *kc, const double *kb, R zpar, double ex_d,
+                                               int rep, R &acc, R &agw)
 {
-    dry_block_soil<R>(s, kc[0], ex_d, rep);
+    dry_block_soil<R>(s, kc[0], zpar, ex_d, rep);
     const double a = static_cast<double>(s.ove), b = static_cast<double>(s.itf);
     const double g = static_cast<double>(s.sgw), w = static_cast<double>(s.riv);
     const double a_n = a * kb[0 * kStride], b_n = b * kb[1 * kStride], g_n = g * kb[2 * kStride];
@@ -570,7 +626,7 @@ __device__ __forceinline__ void fast_wet_hour(MemberState<R> &s, const FastPar<R
     q_in = fma(b.r_sk, s.ove, fma(b.r_fk, s.itf, q_gw));
     s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - s.riv * kc[6 * kStride]) + q_in;
     R in_quick, in_int, in_gw;
-    fast_wet_soil<R, kStride, sizeof(R) == 8>(s, p, b.D, b.omD, carry, ex, hex, mask, in_quick, in_int, in_gw);
+    fast_wet_soil<R, kStride, true>(s, p, b.D, b.omD, carry, ex, hex, mask, in_quick, in_int, in_gw);
     s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - s.ove * b.r_sk) + in_quick;
     s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - s.itf * b.r_fk) + in_int;
     s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
@@ -601,7 +657,7 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
         const BlockPar<R> b = block_par<R, kStride>(kc);
         const R hex = p.Hz * ex;                    // constant over the block
         const unsigned mask = __activemask();       // the lanes walking this wet block together
-        if (kOneFma && !carry.valid) {              // soil total once per block, then carried hour to hour
+        if (!carry.valid) {       // soil total (binary32: sum of deficits) once per block, then carried hour to hour
             carry.tot = soil_total(s);
             carry.valid = true;
         }
@@ -615,7 +671,7 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
         }
         acc = kOneFma ? fma(sum_riv, kc[6 * kStride], acc) : acc + sum_riv * kc[6 * kStride];
     } else {
-        dry_block_fast<R, kStride>(s, kc, kb, ex_d, rep, acc, agw);
+        dry_block_fast<R, kStride>(s, kc, kb, p.z, ex_d, rep, acc, agw);
         carry.valid = false;
     }
 }

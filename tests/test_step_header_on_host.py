@@ -73,3 +73,34 @@ def test_block_sub_mode_matches_oracle(emulator, catchment, oracle_lib, gap, rep
         worst_gw = max(worst_gw, abs(gw.value - gw_ref) / gw_ref)
     assert worst_q < 1e-11, worst_q
     assert worst_gw < 1e-11, worst_gw
+
+
+@pytest.mark.parametrize("mode,label", [(3, "block mode"), (2, "per-step fast")])
+def test_binary32_state_keeps_nse_kge_within_the_bar(emulator, catchment, mode, label):
+    """The FP32 mode of the kernels (binary32 stores, the soil kept as deficits z - level, see
+    fast_wet_soil_deficit) compiled for the host: NSE and KGE of the 40 golden members against the
+    reference's own discharge within 1e-5 absolute (BASELINE.json north_star).  The GPU unit may
+    contract a * b + c differently, so this pins the formulation, not the bits; the GPU tests
+    repeat it over the whole C2 batch and at the C3 length."""
+    from oracle import scores as oscores
+    dp = ctypes.POINTER(ctypes.c_double)
+    emulator.emulate_run_f32.argtypes = emulator.emulate_run.argtypes
+    g = load_golden("runs_members")
+    split = np.array([0.10, 0.15, 0.15, 0.30, 0.30])
+    rain, peva = np.ascontiguousarray(catchment.rain), np.ascontiguousarray(catchment.peva)
+    worst_nse = worst_kge = worst_q = 0.0
+    for i, p in enumerate(g["params"]):
+        q = np.zeros(3653)
+        gw = ctypes.c_double()
+        p = np.ascontiguousarray(p)
+        emulator.emulate_run_f32(mode, catchment.area, 3600.0, 87672, 8760, rain.ctypes.data_as(dp),
+                                 peva.ctypes.data_as(dp), p.ctypes.data_as(dp), 1, 1200 * 0.45, split.ctypes.data_as(dp),
+                                 1, 24, q.ctypes.data_as(dp), ctypes.byref(gw))
+        ref = oscores.objectivefunction((g["q"][i], [g["gw"][i]]), (catchment.obs, [None]))
+        got = oscores.objectivefunction((q, [gw.value]), (catchment.obs, [None]))
+        worst_nse = max(worst_nse, abs(got[0] - ref[0]))
+        worst_kge = max(worst_kge, abs(got[1] - ref[1]))
+        floor = 1e-6 * g["q"][i].max()
+        worst_q = max(worst_q, float(np.max(np.abs(q - g["q"][i]) / np.maximum(g["q"][i], floor))))
+    assert worst_nse < 1e-5 and worst_kge < 1e-5, (label, worst_nse, worst_kge)
+    assert worst_q < 5e-3, (label, worst_q)      # low flows of the range-corner members (floor: 1e-6 of the peak)

@@ -59,6 +59,8 @@ static int emulate(int mode, int rep, double area, double dt, long T, long W, co
     for (int k = 0; k < 6; ++k) s.ly[k] = v[5 + k] * to_mm;
     s.riv = v[11] * to_mm;
     if (mode != 0) { s.ove += s.dra; s.sgw += s.dgw; s.dra = s.dgw = 0; }
+    if (mode >= 2 && sizeof(R) == 4)      // binary32 fast form: the soil as deficits (fast_wet_soil_deficit)
+        for (int k = 0; k < 6; ++k) s.ly[k] = (R)((double)p.z - v[5 + k] * to_mm);
     FastCarry<R> carry; carry.tot = 0; carry.valid = false;
     StepOut<R> o;
     const R qscale = area / (1e3 * dt), mean_scale = area / (1e3 * dt) / (double)gap;
@@ -80,7 +82,7 @@ static int emulate(int mode, int rep, double area, double dt, long T, long W, co
                 if (wet) {
                     if (!carry.valid) { carry.tot = soil_total(s); carry.valid = true; }
                 } else {
-                    dry_block_soil<R>(s, kc[0], ex_d, rep);
+                    dry_block_soil<R>(s, kc[0], fp.z, ex_d, rep);
                     carry.valid = false;
                 }
                 for (int h = 0; h < rep; ++h) {

@@ -45,6 +45,26 @@ def main():
         eng = BatchEngine(rain[5:5 + 24 * 30], peva[5:5 + 24 * 30], [1e8, 2e8, 3e8], 3600.0, 1, report='raw',
                           members_per_catchment=mpc)
         eng.run(params[:3 * mpc], discharge=True, scores=False)
+    # block-sub mode (reports inside a constant-forcing block), single and multi catchment, both precisions
+    for gap, report in ((1, 'raw'), (6, 'summary'), (24, 'raw')):
+        for precision in ('f64', 'f32'):
+            eng = BatchEngine(c.rain[:n:24] * 24.0, c.peva[:n:24] * 24.0, c.area, 3600.0, gap, extra=EXTRA,
+                              warm_up_steps=24 * 5, report=report, precision=precision, forcing_repeat=24)
+            r = eng.run(params, discharge=True, scores=False, gw=True)
+            cases.append(("block-sub gap=%d %s %s" % (gap, report, precision), float(r["gw"].sum())))
+    eng = BatchEngine(rain[::24] * 24.0, peva[::24] * 24.0, [1e8, 2e8, 3e8], 3600.0, 1, extra=EXTRA, report='raw',
+                      members_per_catchment=50, forcing_repeat=24)
+    eng.run(params[:150], discharge=True, scores=False)
+    # member grouping by the library (range/keys/sort/emit kernels), members outside the fast form in
+    # CTAs of their own on the side stream, scores + gw into a [N, 9] block, best member over idle CTAs
+    big = np.resize(g["params"], (4500, 10)).copy()
+    big[::97, 4] = 1.5                         # S > 0.5: needs the branch-faithful form
+    eng = BatchEngine(c.rain[:n], c.peva[:n], c.area, 3600.0, 24, obs=obs, extra=EXTRA, warm_up_steps=24 * 5,
+                      gw_constraint=0.12667)
+    blk = torch.empty((4500, 9), dtype=torch.float64, device='cuda')
+    r = eng.run(big, scores=True, gw=True, best=('KGE', 1), out={'block': blk})
+    cases.append(("grouped batch with wild members", float(r["best"][0])))
+    cases.append(("run_host", float(eng.run_host(big[:300])["gw"].sum())))
     # conditioning of a score table (mask + ordered compaction, radix select + bitonic sort of the
     # winners: shared-memory histograms, atomics, multi-chunk sort) and the device sampler
     from smartpy_b200.montecarlo import conditioning
