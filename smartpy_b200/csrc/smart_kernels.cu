@@ -61,6 +61,9 @@ constexpr int kStepUnroll = SMART_STEP_UNROLL;   // unroll factor of the per-ste
 #ifndef SMART_SLOW_REGS
 #define SMART_SLOW_REGS 128         // branch-faithful kernels (general, fluxes)
 #endif
+#ifndef SMART_MULTI_REGS_F64
+#define SMART_MULTI_REGS_F64 96     // one-warp CTAs of multi-catchment batches (sweep 80..128 in profiles/: 96-128 within 2 %)
+#endif
 #ifndef SMART_LEAN_RATE
 #define SMART_LEAN_RATE 0.94        // throughput of the lean fast kernel relative to the roomy one at steady state
 #endif
@@ -145,10 +148,13 @@ struct KArgs {
     long long n_threads;         // threads of the launch that may carry a member (N, or the length of order)
     long long N, T, W, ld_q, ld_s, ld_g;
     int C, mpc, gap, report_type;
-    int tpc, pad1;               // threads per catchment (multi-catchment): mpc, or mpc padded to whole warps
+    // multi-catchment thread layout (see member_of_thread): whole warps of one catchment first, the
+    // remainders of all catchments packed behind them; tile geometry of the remainder region
+    int full, rem;               // warps / leftover lanes per catchment: mpc = 32 * full + rem
+    int kc_rem, chunk_rem;
+    long long n_full_threads;    // 32 * full * C
     int chunk, kc, use_tma, force_general;
     int has_extra, best_col, best_sign, first_report;
-    int skew, skew_groups;       // start delay of a CTA in cycles per group step, number of groups (0 = none)
     int rep, mode;               // steps per forcing row (1 = one row per step); kModeStep / kModeBlock / kModeBlockSub
     double dt, aar_ro, split[5], gw_constraint;
 };
@@ -261,13 +267,14 @@ struct Smem {
 template <typename R, int kVariant, int BLOCK, bool kSingle, int kMode>
 __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
                                              const FastPar<R> &fp_, const Smem<R, BLOCK> &sm, long long m, bool active,
-                                             int c, int col, int c_base, double area, double &gw_out, StepOut<R> &o)
+                                             int c, int col, int c_base, int kc_cta, int chunk, double area,
+                                             double &gw_out, StepOut<R> &o)
 {
     constexpr bool kFast = kVariant == kVariantFast;
     constexpr bool kWide = sizeof(R) == 8;    // binary64 state: run-long sums stay in registers
     constexpr bool kDaily = kMode != kModeStep;
-    const int kc = kSingle ? 1 : a.kc;
-    const int tile = stage_doubles(a.chunk, kc);
+    const int kc = kSingle ? 1 : kc_cta;
+    const int tile = stage_doubles(chunk, kc);
     const int tid = threadIdx.x;
     double &A = sm.acc[0 * BLOCK + tid];      // sum (s - ebar)
     double &B = sm.acc[1 * BLOCK + tid];      // sum (s - ebar)^2
@@ -282,7 +289,6 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     // rows of the forcing arrays: one per step, or one per block of a.rep steps
     const int rep = kDaily ? a.rep : 1;
     const long long rowsW = a.W / rep, rowsT = a.T / rep;
-    const int chunk = a.chunk;
     const int nWc = static_cast<int>((rowsW + chunk - 1) / chunk);
     const int nTot = nWc + static_cast<int>((rowsT + chunk - 1) / chunk);
     // with one simulation step per reporting step 'raw' and 'summary' coincide (structure.py:190-195)
@@ -339,7 +345,6 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     };
 
     int countdown = 0x7fffffff;   // never fires during the warm-up
-    int r = 0;
     R acc = R(0), agw = R(0), aall = R(0);
     FastCarry<R> carry;
     carry.tot = R(0);
@@ -347,15 +352,27 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     o.q_riv = o.q_gw = o.q_all = R(0);
     o.aeva = o.q_ove = o.q_dra = o.q_int = o.q_sgw = o.q_dgw = R(0);
 
-    // one reporting step (structure.py:188-195 + montecarlo.py:193-203), sval in m3/s
+    // one reporting step (structure.py:188-195 + montecarlo.py:193-203), sval in m3/s.  When reports
+    // fall inside a block (every hour for C4a) the output cursor advances by one row per report
+    // instead of being rebuilt from the report index (a 64-bit multiply-add per store); elsewhere a
+    // report is rare and the index costs one register instead of a pointer.
+    constexpr bool kCursor = kMode == kModeBlockSub;
+    R *q_out = (kCursor && a.discharge != nullptr && active) ? static_cast<R *>(a.discharge) + m : nullptr;
+    int r = 0;
     auto report = [&](R sval) {
         if (!kWide) {   // binary32 state: fold the per-gap sums into binary64
             GN += static_cast<double>(agw);
             GD += static_cast<double>(aall);
             agw = aall = R(0);
         }
-        if (a.discharge != nullptr && active)
+        if (kCursor) {
+            if (q_out != nullptr) {
+                *q_out = sval;
+                q_out += a.ld_q;
+            }
+        } else if (a.discharge != nullptr && active) {
             static_cast<R *>(a.discharge)[static_cast<long long>(r) * a.ld_q + m] = sval;
+        }
         if (a.obs != nullptr) {
             const double e = __ldg(&a.obs[static_cast<long long>(r) * a.C + c]);
             if (e == e) {                            // montecarlo.py:195-196 NaN mask
@@ -432,6 +449,7 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         } else if (kMode == kModeBlockSub) {
             // reports inside the block: every hour hands its outflows to the reporting code below
             const R scale = static_cast<R>(SCALE);           // (not yet set during the warm-up: unused there)
+            const bool in_main = ci >= nWc;
             auto after_hour = [&](R q_riv, R q_gw, R q_all) {
                 acc += q_riv;
                 if (summary) {
@@ -454,46 +472,74 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
                     report(sval);
                 }
             };
-            for (int i = 0; i < n; ++i) {
-                const double rain_i = fr[0], peva_i = fp[0];
-                fr += kc;
-                fp += kc;
-                if constexpr (kFast) {
-                    const double ex_d = __dsub_rn(__dmul_rn(rain_i, *tdp), peva_i);   // structure.py:353-355
-                    const BlockPar<R> bp = block_par<R, BLOCK>(kconst);
-                    const R r_rk = kconst[6 * BLOCK];
-                    if (ex_d >= 0.0) {
-                        const R ex = static_cast<R>(ex_d);
-                        const R hex = fp_.Hz * ex;
-                        const unsigned mask = __activemask();
-                        if (!carry.valid) {
-                            carry.tot = soil_total(s);
-                            carry.valid = true;
-                        }
+            // gap == 1: every step is a report ('raw' and 'summary' coincide) -- no countdown, no
+            // per-gap sum; the fast form keeps the sum of Q_out for the groundwater share
+            auto every_hour = [&](R q_riv, R q_gw, R q_all) {
+                agw += q_gw;
+                if (kFast) {
+                    if (kWide) aall += q_riv;
+                    else acc += q_riv;
+                } else {
+                    aall += q_all;
+                }
+                if (in_main) report(q_riv * scale);
+            };
+            auto rows = [&](auto hourly_tag) {
+                constexpr bool kHourly = decltype(hourly_tag)::value;
+                auto done = [&](R q_riv, R q_gw, R q_all) {
+                    if constexpr (kHourly) every_hour(q_riv, q_gw, q_all);
+                    else after_hour(q_riv, q_gw, q_all);
+                };
+                for (int i = 0; i < n; ++i) {
+                    const double rain_i = fr[0], peva_i = fp[0];
+                    fr += kc;
+                    fp += kc;
+                    if constexpr (kFast) {
+                        const double ex_d = __dsub_rn(__dmul_rn(rain_i, *tdp), peva_i);   // structure.py:353-355
+                        const BlockPar<R> bp = block_par<R, BLOCK>(kconst);
+                        const R r_rk = kconst[6 * BLOCK];
+                        if (ex_d >= 0.0) {
+                            const R ex = static_cast<R>(ex_d);
+                            const R hex = fp_.Hz * ex;
+                            const unsigned mask = __activemask();
+                            if (!carry.valid) {
+                                carry.tot = soil_total(s);
+                                carry.valid = true;
+                            }
 #pragma unroll 2
-                        for (int h = 0; h < rep; ++h) {
-                            const R q_riv = s.riv * r_rk;
-                            R q_gw, q_in;
-                            fast_wet_hour<R, BLOCK>(s, fp_, kconst, bp, carry, ex, hex, mask, q_gw, q_in);
-                            after_hour(q_riv, q_gw, q_in);
+                            for (int h = 0; h < rep; ++h) {
+                                const R q_riv = s.riv * r_rk;
+                                R q_gw, q_in;
+                                fast_wet_hour<R, BLOCK>(s, fp_, kconst, bp, carry, ex, hex, mask, q_gw, q_in);
+                                done(q_riv, q_gw, q_in);
+                            }
+                        } else {
+                            dry_block_soil<R>(s, kconst[0], fp_.z, ex_d, rep);
+                            carry.valid = false;
+#pragma unroll 2
+                            for (int h = 0; h < rep; ++h) {
+                                const R q_riv = s.riv * r_rk;
+                                R q_gw, q_in;
+                                fast_dry_hour<R, BLOCK>(s, fp_, kconst, bp, q_gw, q_in);
+                                done(q_riv, q_gw, q_in);
+                            }
                         }
                     } else {
-                        dry_block_soil<R>(s, kconst[0], fp_.z, ex_d, rep);
-                        carry.valid = false;
-#pragma unroll 2
                         for (int h = 0; h < rep; ++h) {
-                            const R q_riv = s.riv * r_rk;
-                            R q_gw, q_in;
-                            fast_dry_hour<R, BLOCK>(s, fp_, kconst, bp, q_gw, q_in);
-                            after_hour(q_riv, q_gw, q_in);
+                            smart_step<R, true, kVariant == kVariantFluxes>(s, p, rain_i, peva_i, o);
+                            done(o.q_riv, o.q_gw, o.q_all);
                         }
                     }
-                } else {
-                    for (int h = 0; h < rep; ++h) {
-                        smart_step<R, true, kVariant == kVariantFluxes>(s, p, rain_i, peva_i, o);
-                        after_hour(o.q_riv, o.q_gw, o.q_all);
-                    }
                 }
+            };
+            if (a.gap == 1) {
+                rows(std::true_type{});
+                if (!kWide && kFast && in_main) {   // binary32 state: the chunk's sum of Q_out joins the binary64 sum
+                    GD += static_cast<double>(acc);
+                    acc = R(0);
+                }
+            } else {
+                rows(std::false_type{});
             }
         } else {
             // wet/dry driver of the fast step, formed one step ahead of the state
@@ -635,11 +681,12 @@ __device__ __forceinline__ void cta_best(const KArgs &a, double *scratch, double
 
 template <typename R, int kVariant, int BLOCK, bool kSingle, int kMode>
 __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
-                                           long long m, bool active, int c, int col, int c_base, double area)
+                                           long long m, bool active, int c, int col, int c_base, int kc_cta, int chunk,
+                                           double area)
 {
     constexpr bool kFast = kVariant == kVariantFast;
     const int tid = threadIdx.x;
-    const Smem<R, BLOCK> sm(smem_raw, stage_doubles(a.chunk, kSingle ? 1 : a.kc));
+    const Smem<R, BLOCK> sm(smem_raw, stage_doubles(chunk, kSingle ? 1 : kc_cta));
     const double T = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
     const double SK = par[6], FK = par[7], GK = par[8], RK = par[9];
     MemberPar<R> p;
@@ -732,7 +779,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 
     double gw = 0.0;
     StepOut<R> o;
-    run_timeline<R, kVariant, BLOCK, kSingle, kMode>(a, s, p, fp_, sm, m, active, c, col, c_base, area, gw, o);
+    run_timeline<R, kVariant, BLOCK, kSingle, kMode>(a, s, p, fp_, sm, m, active, c, col, c_base, kc_cta, chunk, area, gw, o);
 
     // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
     const double target = write_member_results<BLOCK>(a, sm.acc + tid, m, active, c, gw);
@@ -777,15 +824,31 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
     const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + tid;
     bool active = m_raw < a.n_threads;
     long long m = active ? m_raw : a.n_threads - 1;   // tail threads shadow the last one, store nothing
-    int c = 0;
+    int c = 0, c_base = 0, kc_cta = a.kc, chunk = a.chunk;
     if (!kSingle) {
-        // thread -> (catchment, member of it).  a.tpc threads serve one catchment: a.mpc of them carry
-        // a member, the others (padding up to whole warps, see tpc_of) shadow its last member, so
-        // that no warp mixes the weather of two catchments.
-        c = static_cast<int>(m / a.tpc);
-        const int l = static_cast<int>(m - static_cast<long long>(c) * a.tpc);
-        active = active && l < a.mpc;
-        m = static_cast<long long>(c) * a.mpc + (l < a.mpc ? l : a.mpc - 1);
+        // thread -> (catchment, member).  A warp that holds members of two catchments walks two
+        // weathers: on most days one is wet and the other dry, the warp pays for both paths, and
+        // in a wider CTA the other warps wait for it at the staging barrier (C4a: 22 % of the warp
+        // time at barriers, 27 of 32 lanes active).  So the launch is laid out in two regions:
+        //   [0, n_full_threads)  whole warps of ONE catchment: warp w serves catchment w / full,
+        //                        members 32 (w % full) .. + 31 of it;
+        //   behind them          the mpc % 32 leftover members of every catchment, packed.
+        // Only the second region (mpc % 32 of every mpc members) still mixes catchments; with
+        // one-warp CTAs (launch()) no warp waits for another.
+        const long long cta_first = static_cast<long long>(blockIdx.x) * BLOCK;
+        if (m < a.n_full_threads) {
+            const long long w = m >> 5;
+            c = static_cast<int>(w / a.full);
+            m = static_cast<long long>(c) * a.mpc + ((w - static_cast<long long>(c) * a.full) << 5) + (m & 31);
+            c_base = static_cast<int>((cta_first >> 5) / a.full);
+        } else {
+            const long long r = m - a.n_full_threads;
+            c = static_cast<int>(r / a.rem);
+            m = static_cast<long long>(c) * a.mpc + 32LL * a.full + (r - static_cast<long long>(c) * a.rem);
+            c_base = static_cast<int>((cta_first - a.n_full_threads) / a.rem);
+            kc_cta = a.kc_rem;
+            chunk = a.chunk_rem;
+        }
     }
     if (a.order != nullptr) {
         // (single catchment, no [t][member] output: validate().)  Idle slots hold -1; an idle thread
@@ -805,15 +868,6 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         }
     }
 
-    if (a.skew > 0) {
-        // Every member of a single-catchment batch walks the SAME forcing: CTAs that start together
-        // reach the dry days (closed form, scoring: little FP64 work) and the wet days (FP64-pipe
-        // bound) together, so the sub-partition alternates between an idle and a contended pipe.
-        // CTAs that share an SM start a few days' worth of cycles apart instead.
-        const long long until = clock64() + static_cast<long long>((blockIdx.x / 148) % a.skew_groups) * a.skew;
-        while (clock64() < until) __nanosleep(2000);
-    }
-
     double par[SMART_N_PARAMS];
 #pragma unroll
     for (int k = 0; k < SMART_N_PARAMS; ++k) par[k] = a.params[m * SMART_N_PARAMS + k];
@@ -824,7 +878,6 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         if ((need_general != 0) != (kVariant == kVariantGeneral)) return;   // the other launch owns this CTA
     }
 
-    const int c_base = kSingle ? 0 : static_cast<int>((static_cast<long long>(blockIdx.x) * BLOCK) / a.tpc);
     const int col = c - c_base;
     const double area = a.area[c];
 
@@ -838,7 +891,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         __syncthreads();
     }
 
-    run_member<R, kVariant, BLOCK, kSingle, kMode>(a, smem_raw, par, m, active, c, col, c_base, area);
+    run_member<R, kVariant, BLOCK, kSingle, kMode>(a, smem_raw, par, m, active, c, col, c_base, kc_cta, chunk, area);
 }
 
 __global__ void best_finalize_kernel(const double *blk_score, const long long *blk_index, int n_blocks, int sign,
@@ -992,23 +1045,7 @@ int64_t n_report_of(const smart_batch_desc *d)
                                                   : (d->n_steps + d->report_gap - 1) / d->report_gap;
 }
 
-constexpr int kBlockSmall = 64, kBlockLarge = 128;
-
-// Threads that serve one catchment of a multi-catchment batch.  A warp that holds members of two
-// catchments walks two weathers: on most days one is wet and the other dry, the warp pays for
-// both paths, and the other warps of its CTA wait for it at the staging barrier (C4a measured at
-// twice the cost per member-step of a uniform batch).  When it costs < 50 % more threads, every
-// catchment gets whole warps of its own: members_per_catchment rounded up to a multiple of 32,
-// the extra lanes idle (they shadow the catchment's last member and store nothing).
-int tpc_of(const smart_batch_desc *d)
-{
-    if (d->n_catchments <= 1) return 1;
-    const int mpc = d->members_per_catchment;
-    const int padded = (mpc + 31) / 32 * 32;
-    static const bool off = getenv("SMART_B200_NO_WARP_PADDING") != nullptr;
-    return (!off && 2 * padded <= 3 * mpc) ? padded : mpc;
-}
-
+constexpr int kBlockTiny = 32, kBlockSmall = 64, kBlockLarge = 128;
 
 // Members per CTA.  Members cost the same, so a launch finishes when the SM with the most
 // members does: 64-thread CTAs spread a batch of a few waves more evenly over the 148 SMs
@@ -1021,19 +1058,15 @@ int block_of(const smart_batch_desc *d)
         return e ? atoi(e) : 0;
     }();
     if (forced == kBlockSmall || forced == kBlockLarge) return forced;
-    if (d->n_catchments > 1 && tpc_of(d) != d->members_per_catchment) {
-        // padded catchments: a CTA that holds whole catchments (or part of one) has one pace
-        if (tpc_of(d) % kBlockLarge == 0) return kBlockLarge;
-        if (tpc_of(d) % kBlockSmall == 0 || kBlockSmall % tpc_of(d) == 0) return kBlockSmall;
-    }
+    // multi-catchment batches with whole warps per catchment: one warp per CTA, so that catchments
+    // with different weather never wait for each other at the staging barrier
+    if (d->n_catchments > 1 && d->members_per_catchment >= 32 && !getenv("SMART_B200_NO_WARP_CTAS")) return kBlockTiny;
     return d->n_members <= 148LL * 736 * 8 ? kBlockSmall : kBlockLarge;
 }
 
-// threads of a launch that may carry a member: one per member, one per slot of member_order, or
-// tpc_of() per catchment
+// threads of a launch that may carry a member: one per member, or one per slot of member_order
 int64_t n_threads_of(const smart_batch_desc *d)
 {
-    if (d->n_catchments > 1) return static_cast<int64_t>(d->n_catchments) * tpc_of(d);
     return d->member_order && d->member_order_len > 0 ? d->member_order_len : d->n_members;
 }
 
@@ -1126,7 +1159,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     a.ld_q = d->ld_discharge;
     a.C = d->n_catchments;
     a.mpc = d->n_catchments > 1 ? d->members_per_catchment : 1;
-    a.tpc = d->n_catchments > 1 ? tpc_of(d) : 1;
+
     a.gap = d->report_gap;
     a.report_type = d->report_type;
     a.has_extra = d->has_extra;
@@ -1145,12 +1178,6 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     const int block = block_of(d);
     const int blocks = n_blocks_of(d, block);
     const int mode = mode_of(d);
-    {
-        static const int skew = [] { const char *e = getenv("SMART_B200_SKEW"); return e ? atoi(e) : 0; }();
-        static const int groups = [] { const char *e = getenv("SMART_B200_SKEW_GROUPS"); return e ? atoi(e) : 12; }();
-        a.skew = skew;
-        a.skew_groups = groups > 0 ? groups : 1;
-    }
     const bool daily = mode != kModeStep;
     a.mode = mode;
     a.rep = daily ? d->forcing_repeat : 1;
@@ -1161,21 +1188,35 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
                              (reinterpret_cast<uintptr_t>(d->peva) % 16 == 0);
         a.use_tma = (aligned && !(d->flags & SMART_FLAG_NO_TMA)) ? 1 : 0;
     } else {
-        a.kc = (block % a.tpc == 0 || a.tpc % block == 0) ? (block + a.tpc - 1) / a.tpc   // CTAs aligned with catchments
-                                                          : (block - 1) / a.tpc + 2;      // catchments one CTA can straddle
-        if (a.kc > a.C) a.kc = a.C;
-        int chunk = (12 * 1024) / (2 * 2 * 8 * a.kc);   // 12 KB of forcing stages per CTA
-        chunk = chunk > (daily ? 64 : 512) ? (daily ? 64 : 512) : chunk;
-        chunk &= ~7;
-        if (chunk < 8) return fail(SMART_ERR_BAD_ARG, "members_per_catchment too small for one CTA tile");
-        a.chunk = chunk;
+        // forcing stages per CTA: 12 KB for the wide CTAs, 3 KB for the one-warp CTAs (20 and more of
+        // them share an SM; the stages must not be what limits the resident warps)
+        const int stage_bytes = block == kBlockTiny ? 3 * 1024 : 12 * 1024;
+        auto tile_rows = [&](int kc) {
+            int chunk = stage_bytes / (2 * 2 * 8 * kc);
+            chunk = chunk > (daily ? 64 : 512) ? (daily ? 64 : 512) : chunk;
+            return chunk & ~7;
+        };
+        // thread layout (kernel prologue): whole warps per catchment when the CTA is one warp,
+        // else the members in their own order (every thread in the "leftover" region)
+        a.full = block == kBlockTiny ? a.mpc / 32 : 0;
+        a.rem = a.mpc - 32 * a.full;
+        a.n_full_threads = 32LL * a.full * a.C;
+        a.kc = 1;                                       // whole-warp region: one catchment per CTA
+        a.chunk = tile_rows(1);
+        a.kc_rem = a.rem > 0 ? (block - 1) / a.rem + 2 : 1;   // catchments one CTA of the leftover region can straddle
+        if (a.kc_rem > a.C) a.kc_rem = a.C;
+        a.chunk_rem = tile_rows(a.kc_rem);
+        if (a.rem == 0) a.rem = 1;                      // (region is empty: keep the divisions defined)
+        if (a.chunk_rem < 8) return fail(SMART_ERR_BAD_ARG, "members_per_catchment too small for one CTA tile");
         a.use_tma = 0;
     }
     if (d->best_sign != 0) {
         a.blk_best_score = static_cast<double *>(d->workspace);
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
-    const size_t smem = kSmemHeader + sizeof(double) * (4 * static_cast<size_t>(stage_doubles(a.chunk, a.kc)) + kAccSlots * block) +
+    size_t tile = static_cast<size_t>(stage_doubles(a.chunk, a.kc));
+    if (a.C > 1 && static_cast<size_t>(stage_doubles(a.chunk_rem, a.kc_rem)) > tile) tile = stage_doubles(a.chunk_rem, a.kc_rem);
+    const size_t smem = kSmemHeader + sizeof(double) * (4 * tile + kAccSlots * block) +
                         sizeof(R) * (kConstSlots + 1) * block +
                         sizeof(double) * (1 + (mode == kModeBlock ? kBlockSlots : 0)) * block;
     using Kernel = void (*)(const KArgs);
@@ -1198,8 +1239,13 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         constexpr int B = decltype(block_tag)::value;
         constexpr bool S = decltype(single_tag)::value;
         constexpr int M = decltype(mode_tag)::value;
-        fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S, M>;
-        fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S, M>;
+        if constexpr (B == kBlockTiny) {     // one register budget for the one-warp CTAs
+            constexpr int kMultiRegs = sizeof(R) == 8 ? SMART_MULTI_REGS_F64 : SMART_FAST_REGS_F32;
+            fast_lean = fast_roomy = smart_batch_kernel<R, kVariantFast, B, kMultiRegs, S, M>;
+        } else {
+            fast_lean = smart_batch_kernel<R, kVariantFast, B, kLeanRegs, S, M>;
+            fast_roomy = smart_batch_kernel<R, kVariantFast, B, kRoomyRegs, S, M>;
+        }
         general = smart_batch_kernel<R, kVariantGeneral, B, kSlowRegs, S, M>;
         fluxes = smart_batch_kernel<R, kVariantFluxes, B, kSlowRegs, S, kModeStep>;
     };
@@ -1210,11 +1256,16 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     };
     using BL = std::integral_constant<int, kBlockLarge>;
     using BS = std::integral_constant<int, kBlockSmall>;
-    switch ((block == kBlockLarge ? 2 : 0) | (a.C == 1 ? 1 : 0)) {
-        case 0: pick_mode(BS{}, std::false_type{}); break;
-        case 1: pick_mode(BS{}, std::true_type{}); break;
-        case 2: pick_mode(BL{}, std::false_type{}); break;
-        default: pick_mode(BL{}, std::true_type{}); break;
+    using BT = std::integral_constant<int, kBlockTiny>;
+    if (block == kBlockTiny) {                           // (multi-catchment only: block_of)
+        pick_mode(BT{}, std::false_type{});
+    } else {
+        switch ((block == kBlockLarge ? 2 : 0) | (a.C == 1 ? 1 : 0)) {
+            case 0: pick_mode(BS{}, std::false_type{}); break;
+            case 1: pick_mode(BS{}, std::true_type{}); break;
+            case 2: pick_mode(BL{}, std::false_type{}); break;
+            default: pick_mode(BL{}, std::true_type{}); break;
+        }
     }
     if (d->last_state) {
         if ((rc = go(fluxes, stream))) return rc;
@@ -1300,7 +1351,7 @@ int64_t smart_batch_n_report(const smart_batch_desc *d) { return d ? n_report_of
 size_t smart_batch_workspace_bytes(const smart_batch_desc *d)
 {
     if (!d || d->best_sign == 0) return 0;
-    return static_cast<size_t>(n_blocks_of(d, kBlockSmall)) * (sizeof(double) + sizeof(long long));
+    return static_cast<size_t>(n_blocks_of(d, block_of(d))) * (sizeof(double) + sizeof(long long));
 }
 
 int smart_obs_stats(const double *obs, int64_t n_report, int32_t n_catchments, double *stats, void *stream)

@@ -440,49 +440,21 @@ order_keys_kernel(const double *__restrict__ params, long long n, long long padd
 
 // sorted rows -> slots: fast members at [0, F), idle slots up to the next multiple of kOrderPad,
 // then the members of the branch-faithful form, idle slots to the end.
-//
-// The sorted order is then dealt out in whole CTAs' worth (kOrderPad members) through a fixed
-// bijection of the full groups, g -> g * stride mod n_groups with stride ~ 0.618 n_groups (golden
-// ratio, made coprime with n_groups).  What a member costs varies along the sorted order -- with T
-// (share of wet days) and, inside a slice of T, with S * Z (how often the column saturates and
-// the fill ladder walks all six layers: +30 % per wet hour) -- with a period of N / 64 members.  The
-// hardware hands consecutive CTAs to consecutive SMs, so an SM's CTAs b, b + 148, b + 296 ... sample
-// that periodic cost at a fixed stride, and 148 CTAs is close to a multiple of the period of a
-// 1e5-member batch: some SMs drew mostly expensive CTAs (ncu, C2: the busiest SM 31 % longer than
-// the idlest, 14 % above the mean).  After the bijection neighbouring CTAs come from far-apart places
-// of the order and every stride sees all of it.  Which members share a warp does not change.
-__host__ __device__ inline long long order_group_stride(long long n_groups)
-{
-    if (n_groups < 3) return 1;
-    long long s = (long long)(0.6180339887498949 * (double)n_groups);
-    if (s < 1) s = 1;
-    for (;; ++s) {                     // next value coprime with n_groups (a handful of steps at most)
-        long long a = s, b = n_groups;
-        while (b) {
-            const long long t = a % b;
-            a = b;
-            b = t;
-        }
-        if (a == 1) return s;
-    }
-}
-
+// (Tried and dropped: dealing the CTAs' worth of members out through a golden-ratio bijection so
+// that every SM draws from the whole sorted order.  A C2-sized launch is one wave, every
+// sub-partition keeps its 5 or 6 warps for the whole run and the kernel ends with the slowest one;
+// warps of an LHS batch differ by +-4.5 % in cost, and a random draw of 5-6 of them is WORSE
+// balanced (max/mean 1.20) than neighbours in the sorted order (1.15); measured 28.3 vs 27.7 ms.)
 __global__ void __launch_bounds__(256)
 order_emit_kernel(const unsigned int *__restrict__ cand_row, long long n, long long slots, const OrderState *st,
                   long long *__restrict__ order_out)
 {
     const long long n_fast = st->n_fast;
     const long long general_at = (n_fast + kOrderPad - 1) / kOrderPad * kOrderPad;
-    const long long fast_groups = n_fast / kOrderPad;                 // full groups of the fast form: dealt out
-    const long long stride = order_group_stride(fast_groups);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slots; i += (long long)gridDim.x * blockDim.x) {
         long long src = -1;
-        if (i < n_fast) {
-            const long long g = i / kOrderPad;
-            src = g < fast_groups ? ((g * stride) % fast_groups) * kOrderPad + (i - g * kOrderPad) : i;
-        } else if (i >= general_at && i - general_at < n - n_fast) {
-            src = n_fast + (i - general_at);
-        }
+        if (i < n_fast) src = i;
+        else if (i >= general_at && i - general_at < n - n_fast) src = n_fast + (i - general_at);
         order_out[i] = src < 0 ? -1 : (long long)cand_row[src];
     }
 }
