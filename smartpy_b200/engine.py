@@ -231,7 +231,7 @@ class BatchEngine(object):
                 p_host = p_host[None, :]
             pinned = self._pinned('run_params', p_host.shape, torch.float64)
             torch.cuda.current_stream(dev).synchronize()     # the previous copy out of this buffer is done
-            pinned.numpy()[...] = p_host
+            pinned.copy_(torch.from_numpy(p_host))
             p_dev = pinned.to(dev, non_blocking=True)
         if p_dev.dim() != 2 or p_dev.shape[1] != _native.N_PARAMS:
             raise ValueError("params must be [N, 10]")
@@ -361,7 +361,7 @@ class BatchEngine(object):
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev)
             p_pin = self._pinned('params', p_host.shape, torch.float64)
-            p_pin.numpy()[...] = p_host
+            p_pin.copy_(torch.from_numpy(p_host))            # (torch splits a large host copy over its threads)
             p_dev = self._device_buffer('params', p_host.shape)
             p_dev.copy_(p_pin, non_blocking=True)
             blk = self._device_buffer('block', (n, _native.N_SCORES + 1))
