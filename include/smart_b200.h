@@ -54,6 +54,10 @@ extern "C" {
 #define SMART_FLAG_FORCE_GENERAL 0x1u /* always take the branch-faithful step (clamps, 95% river cap,
                                          leak predicates); default: chosen per CTA from the parameters */
 #define SMART_FLAG_NO_TMA 0x2u        /* stage forcing with plain loads instead of cp.async.bulk */
+/* Tests and tuning: bits 8..15 ask for a relay (see workspace_bytes) of about that many segments
+ * whatever the batch size; 0 = the library decides from the number of waves. */
+#define SMART_FLAG_RELAY_SEGS(n) (((unsigned)(n) & 0xffu) << 8)
+#define SMART_FLAG_RELAY_SEGS_OF(flags) (((flags) >> 8) & 0xffu)
 
 /*
  * One batch of members.  Member m uses params[m][0..9] and catchment
@@ -110,7 +114,8 @@ typedef struct smart_batch_desc {
     int32_t best_sign;              /* 0 = off */
     double *best_score;             /* [1] */
     int64_t *best_index;            /* [1] */
-    void *workspace;                /* smart_batch_workspace_bytes() bytes when best_sign != 0 */
+    void *workspace;                /* device scratch of smart_batch_workspace_bytes() bytes: required when
+                                       best_sign != 0, optional otherwise (see workspace_bytes) */
 
     /* ---- grouping of members into warps (optional, device): a permutation of 0..n_members-1;
      *      thread i of the launch advances member member_order[i] and writes that member's
@@ -130,6 +135,14 @@ typedef struct smart_batch_desc {
      *      with idle slots (-1) to a CTA boundary, then the members that need the branch-faithful
      *      form -- so that no CTA mixes the two. */
     int64_t member_order_len;
+    /* ---- size of `workspace` in bytes.  0 = the caller sized it for the best-member search only
+     *      (the contract before this field existed).  With smart_batch_workspace_bytes() bytes the
+     *      library may run a batch that does not fill many waves as a RELAY: the timeline is cut
+     *      into segments, one CTA advances one group of members through one segment and parks the
+     *      group's state in the workspace for whichever CTA takes the next segment, so that the SMs
+     *      share the work evenly instead of waiting for the slowest warp of a single wave.  Results
+     *      are the same bits either way. */
+    int64_t workspace_bytes;
 } smart_batch_desc;
 
 int smart_version(void);

@@ -28,6 +28,11 @@ ERR_NO_DEVICE = -5
 FLAG_FORCE_GENERAL = 0x1
 FLAG_NO_TMA = 0x2
 
+
+def flag_relay_segs(n):
+    """SMART_FLAG_RELAY_SEGS(n): ask for a relay of about n segments whatever the batch size."""
+    return (int(n) & 0xff) << 8
+
 # every symbol include/smart_b200.h declares
 SYMBOLS = (
     "smart_version", "smart_last_error", "smart_launch_count", "smart_batch_n_report", "smart_batch_workspace_bytes",
@@ -89,6 +94,7 @@ class BatchDesc(ctypes.Structure):
         ("ld_scores", ctypes.c_int64),
         ("ld_gw", ctypes.c_int64),
         ("member_order_len", ctypes.c_int64),
+        ("workspace_bytes", ctypes.c_int64),
     ]
 
 

@@ -47,7 +47,8 @@ constexpr int kChunkSingle = 512;  // forcing steps per smem stage, single catch
 constexpr int kAccSlots = 8;       // per-thread binary64 accumulators parked in smem
 constexpr int kConstSlots = 7;     // per-thread R-typed constants of the fast step parked in smem
 constexpr int kBlockSlots = 7;     // per-thread binary64 constants of the dry-block closed form
-constexpr int kSmemHeader = 128;   // two mbarriers, padded
+constexpr int kSmemHeader = 128;   // two mbarriers, padded (the relay ticket of the CTA sits at byte 32)
+constexpr int kRelaySlots = 26;    // doubles a member parks between two segments of a relay (run_timeline)
 #ifndef SMART_STEP_UNROLL
 #define SMART_STEP_UNROLL 1
 #endif
@@ -156,6 +157,12 @@ struct KArgs {
     int chunk, kc, use_tma, force_general;
     int has_extra, best_col, best_sign, first_report;
     int rep, mode;               // steps per forcing row (1 = one row per step); kModeStep / kModeBlock / kModeBlockSub
+    // relay (see smart_batch_kernel): the timeline in n_seg segments of seg_chunks forcing stages, one CTA
+    // per (segment, group of members); n_seg <= 1: one CTA walks the whole timeline of its group
+    int n_seg, seg_chunks, n_groups;
+    unsigned *relay_ticket;      // order in which the CTAs of this launch came to life
+    int *relay_progress;         // [n_groups] segments of the group that are done
+    double *relay_state;         // [n_groups][kRelaySlots][BLOCK] state parked between segments
     double dt, aar_ro, split[5], gw_constraint;
 };
 
@@ -265,10 +272,10 @@ struct Smem {
 // whole numbers of blocks.  kModeBlock: one row = one reporting step, the fast form advances a
 // whole block at a time (smart_block_fast).  kModeBlockSub: reports fall inside the block.
 template <typename R, int kVariant, int BLOCK, bool kSingle, int kMode>
-__device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
+__device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
                                              const FastPar<R> &fp_, const Smem<R, BLOCK> &sm, long long m, bool active,
                                              int c, int col, int c_base, int kc_cta, int chunk, double area,
-                                             double &gw_out, StepOut<R> &o)
+                                             double &gw_out, StepOut<R> &o, int seg, double *park)
 {
     constexpr bool kFast = kVariant == kVariantFast;
     constexpr bool kWide = sizeof(R) == 8;    // binary64 state: run-long sums stay in registers
@@ -305,11 +312,10 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     };
     // TMA producer (one thread): even element counts go through cp.async.bulk (16-byte
     // granules); an odd tail element is placed with a plain store BEFORE the releasing arrive.
-    auto tma_issue = [&](int ci) {
+    auto tma_issue = [&](int ci, int b) {
         long long t0;
         int n;
         chunk_span(ci, t0, n);
-        const int b = ci & 1;
         double *dr = sm.rain + b * tile, *dp = sm.peva + b * tile;
         const int n_even = n & ~1;
         if (n & 1) {
@@ -324,11 +330,11 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     };
     // generic producer (every thread): rows t0..t0+n, columns c_base..c_base+kc of [rows][C], as
     // asynchronous copies so that the next stage loads while the current one is consumed
-    auto async_issue = [&](int ci) {
+    auto async_issue = [&](int ci, int b) {
         long long t0;
         int n;
         chunk_span(ci, t0, n);
-        double *dr = sm.rain + (ci & 1) * tile, *dp = sm.peva + (ci & 1) * tile;
+        double *dr = sm.rain + b * tile, *dp = sm.peva + b * tile;
         for (int idx = tid; idx < n * kc; idx += BLOCK) {
             const int row = idx / kc, cc = idx - row * kc;
             const int cg = c_base + cc;
@@ -359,6 +365,38 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     constexpr bool kCursor = kMode == kModeBlockSub;
     R *q_out = (kCursor && a.discharge != nullptr && active) ? static_cast<R *>(a.discharge) + m : nullptr;
     int r = 0;
+
+    // Relay: this CTA walks stages [ci_begin, ci_end) of the timeline.  Everything that lives across
+    // a stage boundary -- the twelve stores, the running sums in registers and in shared memory, the
+    // carried soil total, the report countdown and index -- is parked in `park` (one column per
+    // thread, read and written past L1: the previous segment ran on another SM) by the CTA of the
+    // previous segment and picked up here; the numbers and the order of operations on them are
+    // exactly those of one uninterrupted walk.
+    const bool relay = a.n_seg > 1;
+    const int ci_begin = relay ? seg * a.seg_chunks : 0;
+    const int ci_end = relay ? min(nTot, ci_begin + a.seg_chunks) : nTot;
+    if (relay && seg > 0) {
+        const double *pk = park;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s.ly[k] = static_cast<R>(__ldcg(pk + k * BLOCK));
+        s.ove = static_cast<R>(__ldcg(pk + 6 * BLOCK));
+        s.dra = static_cast<R>(__ldcg(pk + 7 * BLOCK));
+        s.itf = static_cast<R>(__ldcg(pk + 8 * BLOCK));
+        s.sgw = static_cast<R>(__ldcg(pk + 9 * BLOCK));
+        s.dgw = static_cast<R>(__ldcg(pk + 10 * BLOCK));
+        s.riv = static_cast<R>(__ldcg(pk + 11 * BLOCK));
+        acc = static_cast<R>(__ldcg(pk + 12 * BLOCK));
+        agw = static_cast<R>(__ldcg(pk + 13 * BLOCK));
+        aall = static_cast<R>(__ldcg(pk + 14 * BLOCK));
+        carry.tot = static_cast<R>(__ldcg(pk + 15 * BLOCK));
+#pragma unroll
+        for (int k = 0; k < kAccSlots; ++k) sm.acc[k * BLOCK + tid] = __ldcg(pk + (16 + k) * BLOCK);
+        const double packed = __ldcg(pk + 24 * BLOCK);
+        countdown = __double2hiint(packed);
+        r = __double2loint(packed);
+        carry.valid = __ldcg(pk + 25 * BLOCK) != 0.0;
+        if (q_out != nullptr) q_out += static_cast<long long>(r) * a.ld_q;
+    }
     auto report = [&](R sval) {
         if (!kWide) {   // binary32 state: fold the per-gap sums into binary64
             GN += static_cast<double>(agw);
@@ -390,22 +428,22 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
     };
 
     if (a.use_tma) {
-        if (tid == 0) tma_issue(0);
+        if (tid == 0) tma_issue(ci_begin, 0);
     } else {
-        async_issue(0);
+        async_issue(ci_begin, 0);
     }
 
-    for (int ci = 0; ci < nTot; ++ci) {
-        const int b = ci & 1;
+    for (int ci = ci_begin, stage = 0; ci < ci_end; ++ci, ++stage) {
+        const int b = stage & 1;
         long long t0;
         int n;
         chunk_span(ci, t0, n);
         if (a.use_tma) {
-            if (tid == 0 && ci + 1 < nTot) tma_issue(ci + 1);
-            mbar_wait(&sm.full[b], static_cast<uint32_t>((ci >> 1) & 1));
+            if (tid == 0 && ci + 1 < ci_end) tma_issue(ci + 1, b ^ 1);
+            mbar_wait(&sm.full[b], static_cast<uint32_t>((stage >> 1) & 1));
         } else {
-            if (ci + 1 < nTot) {
-                async_issue(ci + 1);
+            if (ci + 1 < ci_end) {
+                async_issue(ci + 1, b ^ 1);
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
@@ -585,11 +623,32 @@ __device__ __forceinline__ void run_timeline(const KArgs &a, MemberState<R> &s, 
         }
         __syncthreads();   // every thread is done with stage b before it is refilled
     }
+    if (ci_end < nTot) {   // relay: hand the member over to the CTA of the next segment
+        double *pk = park;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) __stcg(pk + k * BLOCK, static_cast<double>(s.ly[k]));
+        __stcg(pk + 6 * BLOCK, static_cast<double>(s.ove));
+        __stcg(pk + 7 * BLOCK, static_cast<double>(s.dra));
+        __stcg(pk + 8 * BLOCK, static_cast<double>(s.itf));
+        __stcg(pk + 9 * BLOCK, static_cast<double>(s.sgw));
+        __stcg(pk + 10 * BLOCK, static_cast<double>(s.dgw));
+        __stcg(pk + 11 * BLOCK, static_cast<double>(s.riv));
+        __stcg(pk + 12 * BLOCK, static_cast<double>(acc));
+        __stcg(pk + 13 * BLOCK, static_cast<double>(agw));
+        __stcg(pk + 14 * BLOCK, static_cast<double>(aall));
+        __stcg(pk + 15 * BLOCK, static_cast<double>(carry.tot));
+#pragma unroll
+        for (int k = 0; k < kAccSlots; ++k) __stcg(pk + (16 + k) * BLOCK, sm.acc[k * BLOCK + tid]);
+        __stcg(pk + 24 * BLOCK, __hiloint2double(countdown, r));
+        __stcg(pk + 25 * BLOCK, carry.valid ? 1.0 : 0.0);
+        return false;
+    }
     double gn = kWide ? static_cast<double>(agw) : GN;
     double gd = kWide ? static_cast<double>(aall) : GD;
     if (kFast && summary)   // sum of Q_out (block mode and binary32 state keep it in GD) + what the river gained
         gd = ((kWide && kMode != kModeBlock) ? static_cast<double>(aall) : GD) + (static_cast<double>(s.riv) - RIV0);
     gw_out = gn / gd;
+    return true;
 }
 
 // Final objective functions from the shifted sums (montecarlo.py:199-203; formulas of
@@ -645,7 +704,7 @@ __device__ __forceinline__ double write_member_results(const KArgs &a, const dou
 // Arg-max of (target, idx) over the CTA with warp shuffles; ties go to the lower member index.
 // `scratch` = the accumulator slots, free to reuse once every thread has finished its scores.
 template <int kStride>
-__device__ __forceinline__ void cta_best(const KArgs &a, double *scratch, double target, long long idx)
+__device__ __forceinline__ void cta_best(const KArgs &a, double *scratch, double target, long long idx, int blk)
 {
     const int tid = threadIdx.x;
 #pragma unroll
@@ -674,15 +733,15 @@ __device__ __forceinline__ void cta_best(const KArgs &a, double *scratch, double
                 idx = oi;
             }
         }
-        a.blk_best_score[blockIdx.x] = target;
-        a.blk_best_index[blockIdx.x] = idx;
+        a.blk_best_score[blk] = target;
+        a.blk_best_index[blk] = idx;
     }
 }
 
 template <typename R, int kVariant, int BLOCK, bool kSingle, int kMode>
 __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_raw, const double *par,
                                            long long m, bool active, int c, int col, int c_base, int kc_cta, int chunk,
-                                           double area)
+                                           double area, int blk, int seg)
 {
     constexpr bool kFast = kVariant == kVariantFast;
     const int tid = threadIdx.x;
@@ -779,7 +838,19 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 
     double gw = 0.0;
     StepOut<R> o;
-    run_timeline<R, kVariant, BLOCK, kSingle, kMode>(a, s, p, fp_, sm, m, active, c, col, c_base, kc_cta, chunk, area, gw, o);
+    double *park = a.n_seg > 1 ? a.relay_state + (static_cast<long long>(blk) * kRelaySlots) * BLOCK + tid : nullptr;
+    const bool finished = run_timeline<R, kVariant, BLOCK, kSingle, kMode>(a, s, p, fp_, sm, m, active, c, col, c_base,
+                                                                           kc_cta, chunk, area, gw, o, seg, park);
+    if (!finished) {
+        // relay: the group's state is parked; publish that segment `seg` is done (release: the CTA
+        // that takes the next segment acquires this counter before it reads the state)
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.relay_progress + blk), "r"(seg + 1) : "memory");
+        }
+        return;
+    }
 
     // ---- epilogue: scores (montecarlo.py:193-209), gw, last state, best member
     const double target = write_member_results<BLOCK>(a, sm.acc + tid, m, active, c, gw);
@@ -804,7 +875,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
         for (int k = 0; k < 6; ++k) ls[12 + k] = static_cast<double>(s.ly[k]) * to_m3;
         ls[18] = static_cast<double>(s.riv) * to_m3;
     }
-    if (a.best_sign != 0) cta_best<BLOCK>(a, sm.acc, target, active ? m : 0x7fffffffffffffffLL);
+    if (a.best_sign != 0) cta_best<BLOCK>(a, sm.acc, target, active ? m : 0x7fffffffffffffffLL, blk);
 }
 
 // Variant of the step a kernel instantiation carries.  The choice depends on the members'
@@ -821,7 +892,26 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const long long m_raw = static_cast<long long>(blockIdx.x) * BLOCK + tid;
+    // Which group of members, which segment of the timeline.  Plain launch: group = blockIdx.x, the
+    // whole timeline.  Relay (a.n_seg > 1; the grid holds n_groups * n_seg CTAs): a batch that fills
+    // about one wave leaves every SM sub-partition with the 5 or 6 warps it was dealt for the whole
+    // run, and the launch ends with the slowest of them while the others idle (C2: 28 ms against
+    // 21 ms of evenly shared work).  So the timeline is cut into segments and a CTA advances one
+    // group through ONE segment, parking the state for the CTA of the next one.  The hardware's CTA
+    // scheduler then is the work queue: whichever SM frees a slot takes the next (segment, group)
+    // unit.  Units are numbered by a ticket drawn when the CTA comes to life, segment-major, so the
+    // unit a CTA has to wait for (same group, previous segment) always holds a lower ticket: it is
+    // running or done, never waiting for a slot -- no deadlock whatever order the CTAs are placed in.
+    int blk = blockIdx.x, seg = 0;
+    if (a.n_seg > 1) {
+        unsigned *ticket = reinterpret_cast<unsigned *>(smem_raw + 32);
+        if (tid == 0) *ticket = atomicAdd(a.relay_ticket, 1u);
+        __syncthreads();
+        const unsigned t = *ticket;
+        seg = static_cast<int>(t / static_cast<unsigned>(a.n_groups));
+        blk = static_cast<int>(t - static_cast<unsigned>(seg) * static_cast<unsigned>(a.n_groups));
+    }
+    const long long m_raw = static_cast<long long>(blk) * BLOCK + tid;
     bool active = m_raw < a.n_threads;
     long long m = active ? m_raw : a.n_threads - 1;   // tail threads shadow the last one, store nothing
     int c = 0, c_base = 0, kc_cta = a.kc, chunk = a.chunk;
@@ -835,7 +925,7 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         //   behind them          the mpc % 32 leftover members of every catchment, packed.
         // Only the second region (mpc % 32 of every mpc members) still mixes catchments; with
         // one-warp CTAs (launch()) no warp waits for another.
-        const long long cta_first = static_cast<long long>(blockIdx.x) * BLOCK;
+        const long long cta_first = static_cast<long long>(blk) * BLOCK;
         if (m < a.n_full_threads) {
             const long long w = m >> 5;
             c = static_cast<int>(w / a.full);
@@ -853,11 +943,11 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
     if (a.order != nullptr) {
         // (single catchment, no [t][member] output: validate().)  Idle slots hold -1; an idle thread
         // shadows the member of its CTA's first thread, a CTA whose first slot is idle has no member.
-        const long long first = a.order[static_cast<long long>(blockIdx.x) * BLOCK];
+        const long long first = a.order[static_cast<long long>(blk) * BLOCK];
         if (first < 0) {
             if (a.best_sign != 0 && tid == 0) {     // no candidate from this CTA
-                a.blk_best_score[blockIdx.x] = -CUDART_INF;
-                a.blk_best_index[blockIdx.x] = 0x7fffffffffffffffLL;
+                a.blk_best_score[blk] = -CUDART_INF;
+                a.blk_best_index[blk] = 0x7fffffffffffffffLL;
             }
             return;
         }
@@ -881,6 +971,18 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
     const int col = c - c_base;
     const double area = a.area[c];
 
+    if (seg > 0) {   // relay: the previous segment of this group must be done (its state parked)
+        if (tid == 0) {
+            int done;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.relay_progress + blk) : "memory");
+                if (done >= seg) break;
+                __nanosleep(256);
+            }
+        }
+        __syncthreads();
+    }
+
     if (a.use_tma) {
         uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw);
         if (tid == 0) {
@@ -891,7 +993,8 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
         __syncthreads();
     }
 
-    run_member<R, kVariant, BLOCK, kSingle, kMode>(a, smem_raw, par, m, active, c, col, c_base, kc_cta, chunk, area);
+    run_member<R, kVariant, BLOCK, kSingle, kMode>(a, smem_raw, par, m, active, c, col, c_base, kc_cta, chunk, area, blk,
+                                                   seg);
 }
 
 __global__ void best_finalize_kernel(const double *blk_score, const long long *blk_index, int n_blocks, int sign,
@@ -1078,6 +1181,36 @@ int mode_of(const smart_batch_desc *d)
     return (d->report_gap == d->forcing_repeat && d->report_type == SMART_REPORT_SUMMARY) ? kModeBlock : kModeBlockSub;
 }
 
+// ---- relay (see smart_batch_kernel): which batches may run as one, and the scratch they need
+// workspace layout: [best member: blocks * 16 bytes][relay header: 2 tickets, padded to 128 bytes]
+//                   [progress: int per group, padded to 128][state: groups * kRelaySlots * block doubles]
+constexpr int64_t kRelayMaxThreads = 148LL * 640 * 32;  // (scratch: 208 bytes per thread)
+bool relay_possible(const smart_batch_desc *d)
+{
+    static const bool off = [] {
+        const char *e = getenv("SMART_B200_RELAY");
+        return e != nullptr && e[0] == '0';
+    }();
+    return !off && d->n_catchments == 1 && !d->last_state && !d->initial_state && n_threads_of(d) <= kRelayMaxThreads;
+}
+size_t best_workspace_bytes(const smart_batch_desc *d, int blocks)
+{
+    return d->best_sign != 0 ? static_cast<size_t>(blocks) * (sizeof(double) + sizeof(long long)) : 0;
+}
+size_t pad128(size_t n) { return (n + 127) & ~static_cast<size_t>(127); }
+size_t relay_workspace_bytes(int blocks, int block)
+{
+    return 128 + pad128(sizeof(int) * static_cast<size_t>(blocks)) +
+           sizeof(double) * static_cast<size_t>(blocks) * kRelaySlots * block;
+}
+// forcing stages the timeline of a launch is made of (run_timeline: nWc + main stages)
+int n_stages_of(const smart_batch_desc *d, int chunk, int rep)
+{
+    const int64_t W = d->initial_state ? 0 : d->n_warmup;
+    const int64_t rowsW = W / rep, rowsT = d->n_steps / rep;
+    return static_cast<int>((rowsW + chunk - 1) / chunk + (rowsT + chunk - 1) / chunk);
+}
+
 int validate(const smart_batch_desc *d, bool host_mode = false)
 {
     if (!d) return fail(SMART_ERR_BAD_ARG, "descriptor is NULL");
@@ -1214,16 +1347,22 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
         a.blk_best_score = static_cast<double *>(d->workspace);
         a.blk_best_index = reinterpret_cast<long long *>(a.blk_best_score + blocks);
     }
+    a.n_seg = 1;
+    a.n_groups = blocks;
     size_t tile = static_cast<size_t>(stage_doubles(a.chunk, a.kc));
     if (a.C > 1 && static_cast<size_t>(stage_doubles(a.chunk_rem, a.kc_rem)) > tile) tile = stage_doubles(a.chunk_rem, a.kc_rem);
     const size_t smem = kSmemHeader + sizeof(double) * (4 * tile + kAccSlots * block) +
                         sizeof(R) * (kConstSlots + 1) * block +
                         sizeof(double) * (1 + (mode == kModeBlock ? kBlockSlots : 0)) * block;
     using Kernel = void (*)(const KArgs);
-    auto go = [&](Kernel kernel, cudaStream_t st) -> int {
+    unsigned *tickets = nullptr;       // relay: one ticket counter per kernel of the call
+    auto go = [&](Kernel kernel, cudaStream_t st, int which = 0) -> int {
         if (smem > 48 * 1024)   // above the default dynamic shared memory limit: opt in per kernel
             SMART_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        kernel<<<blocks, block, smem, st>>>(a);
+        KArgs b = a;
+        b.relay_ticket = tickets ? tickets + which : nullptr;
+        const long long grid = static_cast<long long>(blocks) * (a.n_seg > 1 ? a.n_seg : 1);
+        kernel<<<static_cast<unsigned>(grid), block, smem, st>>>(b);
         SMART_CUDA(cudaGetLastError());
         count_launches(1);
         return SMART_OK;
@@ -1231,6 +1370,53 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     // Fast kernel: two register budgets are compiled.  The roomy one (no spills) is quicker per
     // wave; the lean one keeps more CTAs resident, which wins when it saves the batch a ragged
     // last wave (config C2: 1e5 members are 1.06 waves at 90 registers, 0.88 at 80).
+    // Relay: decided from how many waves the launch would be with `kernel`; lays out the scratch
+    // behind the best-member slots and clears the tickets and progress counters on the caller's stream.
+    auto try_relay = [&](Kernel kernel) -> int {     // 1 = on, 0 = off, < 0 = error
+        static const double min_waves = [] {
+            const char *e = getenv("SMART_B200_RELAY_MIN_WAVES");
+            return e ? atof(e) : 0.15;
+        }();
+        static const int forced_segs = [] {
+            const char *e = getenv("SMART_B200_RELAY_SEGS");
+            return e ? atoi(e) : 0;
+        }();
+        if (!relay_possible(d) || d->workspace == nullptr) return 0;
+        const size_t head = pad128(best_workspace_bytes(d, blocks));
+        if (d->workspace_bytes < 0 || static_cast<size_t>(d->workspace_bytes) < head + relay_workspace_bytes(blocks, block)) return 0;
+        int dev = 0, sms = 0, per_sm = 0;
+        SMART_CUDA(cudaGetDevice(&dev));
+        SMART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        SMART_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem));
+        if (per_sm < 1) return 0;
+        const double waves = static_cast<double>(blocks) / (static_cast<double>(per_sm) * sms);
+        const int asked = static_cast<int>(SMART_FLAG_RELAY_SEGS_OF(d->flags));   // tests and tuning: any batch size
+        static const double max_waves = [] {
+            const char *e = getenv("SMART_B200_RELAY_MAX_WAVES");
+            return e ? atof(e) : 64.0;
+        }();
+        if (asked == 0 && (waves < min_waves || waves >= max_waves)) return 0;
+        const int n_stages = n_stages_of(d, a.chunk, a.rep);
+        // about 32 units per slot of the GPU; batches of many waves are balanced by the CTA scheduler
+        // already and gain a last 2 % from 8 segments (C3: 764 -> 750 ms)
+        int want = asked > 0 ? asked : forced_segs > 0 ? forced_segs : static_cast<int>(ceil(32.0 / waves));
+        if (asked == 0 && forced_segs == 0 && want < 8) want = 8;
+        if (want > n_stages) want = n_stages;
+        if (want < 2) return 0;
+        a.seg_chunks = (n_stages + want - 1) / want;
+        a.n_seg = (n_stages + a.seg_chunks - 1) / a.seg_chunks;
+        if (a.n_seg < 2) {
+            a.n_seg = 1;
+            return 0;
+        }
+        char *base = static_cast<char *>(d->workspace) + head;
+        tickets = reinterpret_cast<unsigned *>(base);
+        a.relay_progress = reinterpret_cast<int *>(base + 128);
+        const size_t clear = 128 + pad128(sizeof(int) * static_cast<size_t>(blocks));
+        a.relay_state = reinterpret_cast<double *>(base + clear);
+        SMART_CUDA(cudaMemsetAsync(base, 0, clear, stream));
+        return 1;
+    };
     constexpr int kLeanRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64_LEAN : SMART_FAST_REGS_F32;
     constexpr int kRoomyRegs = sizeof(R) == 8 ? SMART_FAST_REGS_F64 : SMART_FAST_REGS_F32;
     constexpr int kSlowRegs = SMART_SLOW_REGS;
@@ -1270,10 +1456,13 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     if (d->last_state) {
         if ((rc = go(fluxes, stream))) return rc;
     } else if (a.force_general || d->initial_state) {
-        if ((rc = go(general, stream))) return rc;
+        if ((rc = try_relay(general)) < 0) return rc;
+        if ((rc = go(general, stream, 1))) return rc;
     } else {
         Kernel fast = fast_roomy;
-        if (fast_lean != fast_roomy) {
+        const int relayed = try_relay(fast_roomy);    // a relay is many waves of short CTAs: the roomy kernel
+        if (relayed < 0) return relayed;
+        if (!relayed && fast_lean != fast_roomy) {
             int dev = 0, sms = 0, per_sm_lean = 0, per_sm_roomy = 0;
             SMART_CUDA(cudaGetDevice(&dev));
             SMART_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1290,6 +1479,8 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
             };
             if (per_sm_lean > 0 && per_sm_roomy > 0 && cost(per_sm_lean, kLeanRate) < cost(per_sm_roomy, 1.0))
                 fast = fast_lean;
+        }
+        if (fast_lean != fast_roomy) {
             static const int forced = [] {
                 const char *e = getenv("SMART_B200_FAST_REGS");   // kernel tuning: "lean" | "roomy"
                 return e ? (e[0] == 'l' ? 1 : 2) : 0;
@@ -1306,13 +1497,13 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
             std::lock_guard<std::mutex> hold(side->mu);
             SMART_CUDA(cudaEventRecord(side->fork, stream));
             SMART_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-            if ((rc = go(general, side->stream))) return rc;
+            if ((rc = go(general, side->stream, 1))) return rc;
             SMART_CUDA(cudaEventRecord(side->join, side->stream));
-            if ((rc = go(fast, stream))) return rc;
+            if ((rc = go(fast, stream, 0))) return rc;
             SMART_CUDA(cudaStreamWaitEvent(stream, side->join, 0));
         } else {
-            if ((rc = go(fast, stream))) return rc;
-            if ((rc = go(general, stream))) return rc;
+            if ((rc = go(fast, stream, 0))) return rc;
+            if ((rc = go(general, stream, 1))) return rc;
         }
     }
     if (d->best_sign != 0) {
@@ -1350,8 +1541,10 @@ int64_t smart_batch_n_report(const smart_batch_desc *d) { return d ? n_report_of
 
 size_t smart_batch_workspace_bytes(const smart_batch_desc *d)
 {
-    if (!d || d->best_sign == 0) return 0;
-    return static_cast<size_t>(n_blocks_of(d, block_of(d))) * (sizeof(double) + sizeof(long long));
+    if (!d || d->n_members < 1) return 0;
+    const int block = block_of(d), blocks = n_blocks_of(d, block);
+    const size_t best = best_workspace_bytes(d, blocks);
+    return relay_possible(d) ? pad128(best) + relay_workspace_bytes(blocks, block) : best;
 }
 
 int smart_obs_stats(const double *obs, int64_t n_report, int32_t n_catchments, double *stats, void *stream)
@@ -1482,7 +1675,8 @@ int smart_batch_run_host(const smart_batch_desc *h, int precision, int device)
     const size_t b_obs = h->obs ? sizeof(double) * n_rep * C : 0, b_stats = h->obs ? sizeof(double) * C * SMART_OBS_STATS : 0;
     const size_t b_q = h->discharge ? q_elem * n_rep * N : 0, b_scores = h->scores ? sizeof(double) * N * SMART_N_SCORES : 0;
     const size_t b_gw = h->gw ? sizeof(double) * N : 0, b_last = h->last_state ? sizeof(double) * N * SMART_N_VARS : 0;
-    const size_t b_ws = h->best_sign != 0 ? smart_batch_workspace_bytes(h) + 16 : 0;
+    const size_t b_ws_lib = smart_batch_workspace_bytes(h);
+    const size_t b_ws = b_ws_lib > 0 ? pad128(b_ws_lib) + 128 : 0;
     const size_t sizes[] = {b_params, b_forcing, b_forcing, b_area, b_init, b_obs, b_stats, b_q, b_scores, b_gw, b_last, b_ws};
     size_t need = 0;
     for (size_t b : sizes) need += (b + 255) & ~static_cast<size_t>(255);
@@ -1536,11 +1730,12 @@ int smart_batch_run_host(const smart_batch_desc *h, int precision, int device)
         d.ld_gw = 1;
     }
     if (h->last_state) d.last_state = static_cast<double *>(ar.take(b_last));
-    if (h->best_sign != 0) {
+    if (b_ws > 0) {
         char *ws = static_cast<char *>(ar.take(b_ws));
         d.best_score = reinterpret_cast<double *>(ws);
         d.best_index = reinterpret_cast<int64_t *>(ws + 8);
-        d.workspace = ws + 16;
+        d.workspace = ws + 128;
+        d.workspace_bytes = static_cast<int64_t>(b_ws - 128);
     }
     rc = precision == 64 ? launch<double>(&d, st) : smart_batch_run_f32(&d, st);
     if (rc) return rc;

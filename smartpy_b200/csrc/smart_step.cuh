@@ -314,7 +314,11 @@ __device__ __forceinline__ void fast_wet_soil_deficit(MemberState<float> &s, con
     };
 #ifndef SMART_NO_EARLY_OUT
     const bool done = fill(0);
+#ifdef SMART_VOTED_EARLY_OUT
     if (__any_sync(mask, !done)) {
+#else
+    if (!done) {                                    // (a lane's own branch: no vote, no mask to carry)
+#endif
         fill(1); fill(2); fill(3); fill(4); fill(5);
     }
 #else
@@ -380,7 +384,11 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
 #ifndef SMART_NO_EARLY_OUT
     // most often the first layer takes everything for every member of the warp
     const bool done = fill(0);
+#ifdef SMART_VOTED_EARLY_OUT
     if (__any_sync(mask, !done)) {
+#else
+    if (!done) {                                    // (a lane's own branch: no vote, no mask to carry)
+#endif
         fill(1); fill(2); fill(3); fill(4); fill(5);
     }
 #else
@@ -440,7 +448,7 @@ __device__ __forceinline__ void fast_dry_soil(MemberState<R> &s, R C, R d, R z)
     };
 #ifndef SMART_NO_EARLY_OUT
     const bool done = take(0);
-    if (__any_sync(__activemask(), !done)) {
+    if (!done) {
         take(1); take(2); take(3); take(4); take(5);
     }
 #else
@@ -529,8 +537,8 @@ __device__ __forceinline__ void dry_block_soil(MemberState<R> &s, R Cpar, R zpar
     for (int k = 0; k < 6; ++k) ly[k] = kDeficits ? z - static_cast<double>(s.ly[k]) : static_cast<double>(s.ly[k]);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        if (__any_sync(__activemask(), left > 0.0)) {
-            if (left > 0.0) {
+        {
+            if (left > 0.0) {                    // (a lane's own branch: lanes that are done skip the layer)
                 bool moves_on = true;            // the demand reaches layer k + 1
                 if (ly[k] > 0.0) {
                     // Level if the layer served every remaining step.  Not negative <=> the exact

@@ -21,6 +21,7 @@ SCORE_NAMES = ['NSE', 'KGE', 'KGEc', 'KGEa', 'KGEb', 'PBias', 'RMSE', 'GW']
 # engine-level flag (not passed to the library): always hand the kernel one forcing row per step
 FLAG_NO_BLOCK_MODE = 0x10000
 FLAG_NO_REORDER = 0x20000     # engine-level: keep the members in sample order inside the launch
+FLAG_NO_RELAY = 0x40000       # engine-level: no launch scratch for the relay (one CTA walks a group's whole timeline)
 REORDER_MIN_MEMBERS = 4096    # below this the sort costs more than the divergence it removes
 
 
@@ -71,6 +72,7 @@ class BatchEngine(object):
         self.extra = extra
         self.gw_constraint = gw_constraint
         self._order_work = {}     # per stream: (workspace, order slots) of smart_member_order
+        self._launch_work = {}    # per stream: scratch of smart_batch_run_* (smart_batch_workspace_bytes)
         self._staging = {}        # persistent pinned host buffers of run_host(), by name
 
         rain = torch.as_tensor(np.ascontiguousarray(rain, dtype=np.float64) if not torch.is_tensor(rain) else rain)
@@ -303,20 +305,31 @@ class BatchEngine(object):
                 column, sign = best
                 d.best_column = SCORE_NAMES.index(column) if isinstance(column, str) else int(column)
                 d.best_sign = 1 if sign > 0 else -1
-                ws_bytes = self.lib.smart_batch_workspace_bytes(ctypes.byref(d))
-                ws = torch.empty((max(ws_bytes, 8) + 7) // 8, dtype=torch.float64, device=dev)
                 bs = torch.empty(1, dtype=torch.float64, device=dev)
                 bi = torch.empty(1, dtype=torch.int64, device=dev)
-                d.workspace = ws.data_ptr()
                 d.best_score = bs.data_ptr()
                 d.best_index = bi.data_ptr()
-                keep.append(ws)
                 res['best'] = (bs, bi)
+            # scratch of the launch: per-CTA winners of the best-member search and, for batches of a
+            # few waves, the state the relay parks between two segments of the timeline (smart_b200.h)
+            ws_bytes = int(self.lib.smart_batch_workspace_bytes(ctypes.byref(d)))
+            if ws_bytes > 0 and (best or not (self.flags & FLAG_NO_RELAY)):
+                ws = self._workspace(ws_bytes, stream)
+                d.workspace = ws.data_ptr()
+                d.workspace_bytes = 0 if (self.flags & FLAG_NO_RELAY) else ws.numel()
             rc = fn(ctypes.byref(d), stream.cuda_stream)
         _native.check(rc)
         for t in keep:   # keep inputs alive until the stream has consumed them
             t.record_stream(stream)
         return res
+
+    def _workspace(self, nbytes, stream):
+        """Launch scratch, kept per stream (runs on one stream are ordered) and grown on demand."""
+        torch = _torch()
+        ws = self._launch_work.get(stream.cuda_stream)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._launch_work[stream.cuda_stream] = torch.empty((nbytes,), dtype=torch.uint8, device=self.device)
+        return ws
 
     def _member_order(self, p_dev, n, stream):
         """Slots of the launch (smart_member_order): members grouped so that the lanes of a warp take
