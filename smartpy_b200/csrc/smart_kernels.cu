@@ -53,6 +53,7 @@ constexpr int kRelaySlots = 26;    // doubles a member parks between two segment
 #define SMART_STEP_UNROLL 1
 #endif
 constexpr int kStepUnroll = SMART_STEP_UNROLL;   // unroll factor of the per-step time loop
+constexpr bool kSubNested = false;               // fill ladder of the hours that report (block-sub mode): one branch for the lower five layers
 #ifndef SMART_FAST_REGS_F64
 #define SMART_FAST_REGS_F64 96     // register budget of the fast FP64 kernel (sweep 80..104 in profiles/): 20 warps per SM, no spills
 #endif
@@ -353,7 +354,7 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
     int countdown = 0x7fffffff;   // never fires during the warm-up
     R acc = R(0), agw = R(0), aall = R(0);
     FastCarry<R> carry;
-    carry.tot = R(0);
+    carry.tot = carry.part = R(0);
     carry.valid = false;
     o.q_riv = o.q_gw = o.q_all = R(0);
     o.aeva = o.q_ove = o.q_dra = o.q_int = o.q_sgw = o.q_dgw = R(0);
@@ -395,6 +396,7 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
         countdown = __double2hiint(packed);
         r = __double2loint(packed);
         carry.valid = __ldcg(pk + 25 * BLOCK) != 0.0;
+        if (sizeof(R) == 8) carry.part = soil_lower(s);   // (what it held: the same five values in the same order)
         if (q_out != nullptr) q_out += static_cast<long long>(r) * a.ld_q;
     }
     auto report = [&](R sval) {
@@ -466,7 +468,7 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
             for (int i = 0; i < n; ++i) {
                 const double ex_d = __dsub_rn(__dmul_rn(fr[0], *tdp), fp[0]);   // structure.py:353-355
                 if constexpr (kFast) {
-                    smart_block_fast<R, BLOCK>(s, fp_, kconst, sm.kblock + tid, carry, ex_d, rep, acc, agw);
+                    smart_block_fast<R, BLOCK, kSingle>(s, fp_, kconst, sm.kblock + tid, carry, ex_d, rep, acc, agw);
                 } else {
                     for (int h = 0; h < rep; ++h) {
                         smart_step<R, true, kVariant == kVariantFluxes>(s, p, fr[0], fp[0], o);
@@ -540,15 +542,12 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
                             const R ex = static_cast<R>(ex_d);
                             const R hex = fp_.Hz * ex;
                             const unsigned mask = __activemask();
-                            if (!carry.valid) {
-                                carry.tot = soil_total(s);
-                                carry.valid = true;
-                            }
+                            if (!carry.valid) carry_form(s, carry);
 #pragma unroll 2
                             for (int h = 0; h < rep; ++h) {
                                 const R q_riv = s.riv * r_rk;
                                 R q_gw, q_in;
-                                fast_wet_hour<R, BLOCK>(s, fp_, kconst, bp, carry, ex, hex, mask, q_gw, q_in);
+                                fast_wet_hour<R, BLOCK, kSubNested>(s, fp_, kconst, bp, carry, ex, hex, mask, q_gw, q_in);
                                 done(q_riv, q_gw, q_in);
                             }
                         } else {

@@ -249,20 +249,38 @@ struct FastPar {
 template <typename R>
 struct FastCarry {
     R tot;          // soil total at the end of the previous step, valid iff that step was wet
+    R part;         // binary64 only: the part of it that layers 2..6 hold (soil_lower), valid with tot
     bool valid;
 };
 
-// Soil total, left to right like the reference's sum() (structure.py:350).  SMART_TOT_TREE
-// switches to a depth-3 tree (same five additions, 25 instead of 41 cycles of dependent
-// latency); measured on B200 it makes no difference, so the reference's order is the default.
+// Soil total of the fast form.  Binary64: from the bottom layer up, the top layer LAST -- on most
+// wet hours the rain only reaches the top layer, and the total after the fill is then the carried
+// sum of the other five plus the new top level: one addition instead of five, and the very number
+// a full re-summation gives (so that a zero leak still comes out as exactly zero).  The
+// branch-faithful step keeps the reference's order (structure.py:350); the two orders differ by an
+// ulp of the total.  Binary32 (sum of deficits): plain left to right, as before.
+template <typename R>
+__device__ __forceinline__ R soil_lower(const MemberState<R> &s)
+{
+    return (((s.ly[5] + s.ly[4]) + s.ly[3]) + s.ly[2]) + s.ly[1];
+}
 template <typename R>
 __device__ __forceinline__ R soil_total(const MemberState<R> &s)
 {
-#ifndef SMART_TOT_TREE
-    return ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
-#else
-    return ((s.ly[0] + s.ly[1]) + (s.ly[2] + s.ly[3])) + (s.ly[4] + s.ly[5]);
-#endif
+    if constexpr (sizeof(R) == 8) return soil_lower(s) + s.ly[0];
+    else return ((((s.ly[0] + s.ly[1]) + s.ly[2]) + s.ly[3]) + s.ly[4]) + s.ly[5];
+}
+// (Re)form the carried sums from the state: the same numbers the carry holds after a wet step.
+template <typename R>
+__device__ __forceinline__ void carry_form(const MemberState<R> &s, FastCarry<R> &c)
+{
+    if constexpr (sizeof(R) == 8) {
+        c.part = soil_lower(s);
+        c.tot = c.part + s.ly[0];
+    } else {
+        c.tot = soil_total(s);
+    }
+    c.valid = true;
 }
 
 
@@ -312,18 +330,11 @@ __device__ __forceinline__ void fast_wet_soil_deficit(MemberState<float> &s, con
         u = fits ? 0.0f : t;
         return fits;
     };
-#ifndef SMART_NO_EARLY_OUT
-    const bool done = fill(0);
-#ifdef SMART_VOTED_EARLY_OUT
-    if (__any_sync(mask, !done)) {
-#else
-    if (!done) {                                    // (a lane's own branch: no vote, no mask to carry)
-#endif
+    // most often the first layer takes everything; a lane's own branch (round 1 voted over the warp:
+    // four more instructions per hour, and the lanes that are done would run the ladder as no-ops)
+    if (!fill(0)) {
         fill(1); fill(2); fill(3); fill(4); fill(5);
     }
-#else
-    fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
-#endif
     in_quick = fma(D, -u, in_quick);                // + D * saturation excess (:376)
     const float sp = p.Sz * tot;                    // :379
     float pw[6];
@@ -354,7 +365,10 @@ __device__ __forceinline__ void fast_wet_soil_deficit(MemberState<float> &s, con
     carry.valid = true;
 }
 
-template <typename R, int kStride, bool kTotKnown = false>
+// kNestedLadder: one early exit per layer of the fill ladder instead of one for the lower five.
+// Measured on B200 (profiles/r02_variant_sweep.txt): +1.7 % for single-catchment block mode (C3), -4 % for
+// the one-warp CTAs of multi-catchment batches (C4b), -1 % per step -- so only the first uses it.
+template <typename R, int kStride, bool kTotKnown = false, bool kNestedLadder = false>
 __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R> &p, R D, R omD,
                                               FastCarry<R> &carry, R ex, R hex, unsigned mask, R &in_quick, R &in_int,
                                               R &in_gw)
@@ -364,10 +378,13 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
         return;
     }
     const R zero = R(0);
-    R tot = carry.tot;
+    R tot = carry.tot, lower = carry.part;
     if (!kTotKnown) {
         if (__any_sync(mask, !carry.valid)) {
-            if (!carry.valid) tot = soil_total(s);
+            if (!carry.valid) {
+                lower = soil_lower(s);
+                tot = lower + s.ly[0];
+            }
         }
     }
     in_quick = hex * tot;                           // :363-364, h' * excess = (H/Z * excess) * total
@@ -381,19 +398,22 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
         u = fits ? zero : t;
         return fits;
     };
-#ifndef SMART_NO_EARLY_OUT
-    // most often the first layer takes everything for every member of the warp
-    const bool done = fill(0);
-#ifdef SMART_VOTED_EARLY_OUT
-    if (__any_sync(mask, !done)) {
-#else
-    if (!done) {                                    // (a lane's own branch: no vote, no mask to carry)
-#endif
-        fill(1); fill(2); fill(3); fill(4); fill(5);
+    // most often the first layer takes everything; a lane's own branches (no vote, no mask to carry)
+    if (!fill(0)) {
+        if (kNestedLadder) {
+            // one branch per layer: the water stops at the first layer with room
+            if (!fill(1)) {
+                if (!fill(2)) {
+                    if (!fill(3)) {
+                        if (!fill(4)) fill(5);
+                    }
+                }
+            }
+        } else {
+            fill(1); fill(2); fill(3); fill(4); fill(5);
+        }
+        lower = soil_lower(s);                      // the rain went below the top layer: re-sum the lower five
     }
-#else
-    fill(0); fill(1); fill(2); fill(3); fill(4); fill(5);
-#endif
     in_quick = fma(D, -u, in_quick);                // + D * saturation excess (:376)
     in_int = omD * (-u);                            // (1 - D) * saturation excess (:377)
     const R sp = p.Sz * tot;                        // :379
@@ -405,8 +425,9 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
     pw[4] = pw[3] * sp;
     pw[5] = pw[2] * pw[2];
     {
-        // soil total after the fill, summed like tot1/tot3 so that a zero leak gives exactly 0
-        const R tot_f = soil_total(s);
+        // soil total after the fill: the lower five layers as carried (or re-summed above when the
+        // rain reached them) plus the new top level -- the number soil_total(s) would give
+        const R tot_f = lower + s.ly[0];
 #pragma unroll
         for (int i = 0; i < 6; ++i) s.ly[i] = fma(-s.ly[i], pw[i], s.ly[i]);            // :381-385
         const R tot1 = soil_total(s);
@@ -418,9 +439,11 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
         }
 #pragma unroll
         for (int i = 5; i >= 0; --i) s.ly[i] = fma(-s.ly[i], pw[5 - i], s.ly[i]);
-        const R tot3 = soil_total(s);
+        const R lower3 = soil_lower(s);
+        const R tot3 = lower3 + s.ly[0];
         in_gw = tot1 - tot3;
         carry.tot = tot3;
+        carry.part = lower3;
         carry.valid = true;
     }
 }
@@ -446,14 +469,9 @@ __device__ __forceinline__ void fast_dry_soil(MemberState<R> &s, R C, R d, R z)
             return enough;
         }
     };
-#ifndef SMART_NO_EARLY_OUT
-    const bool done = take(0);
-    if (!done) {
+    if (!take(0)) {                                 // (a lane's own branch, see fast_wet_soil)
         take(1); take(2); take(3); take(4); take(5);
     }
-#else
-    take(0); take(1); take(2); take(3); take(4); take(5);
-#endif
 }
 
 // One hour of the fast step.  ex_d = rain * T - peva (structure.py:353-355, two separately
@@ -625,7 +643,7 @@ __device__ __forceinline__ BlockPar<R> block_par(const R *kc)
 // share) and the river inflow as one fused dot product r_sk V_quick + r_fk V_int + Q_gw (:254) --
 // river, soil, stores.  The caller reads the river store BEFORE the call (its outflow is
 // r_rk * that value).  carry.tot must be valid (kTotKnown).
-template <typename R, int kStride>
+template <typename R, int kStride, bool kNestedLadder = false>
 __device__ __forceinline__ void fast_wet_hour(MemberState<R> &s, const FastPar<R> &p, const R *kc, const BlockPar<R> &b,
                                               FastCarry<R> &carry, R ex, R hex, unsigned mask, R &q_gw, R &q_in)
 {
@@ -634,7 +652,7 @@ __device__ __forceinline__ void fast_wet_hour(MemberState<R> &s, const FastPar<R
     q_in = fma(b.r_sk, s.ove, fma(b.r_fk, s.itf, q_gw));
     s.riv = kOneFma ? fma(s.riv, p.c_rk, q_in) : (s.riv - s.riv * kc[6 * kStride]) + q_in;
     R in_quick, in_int, in_gw;
-    fast_wet_soil<R, kStride, true>(s, p, b.D, b.omD, carry, ex, hex, mask, in_quick, in_int, in_gw);
+    fast_wet_soil<R, kStride, true, kNestedLadder>(s, p, b.D, b.omD, carry, ex, hex, mask, in_quick, in_int, in_gw);
     s.ove = kOneFma ? fma(s.ove, p.c_sk, in_quick) : (s.ove - s.ove * b.r_sk) + in_quick;
     s.itf = kOneFma ? fma(s.itf, p.c_fk, in_int) : (s.itf - s.itf * b.r_fk) + in_int;
     s.sgw = kOneFma ? fma(s.sgw, p.c_gk, in_gw) : (s.sgw - q_gw) + in_gw;
@@ -655,7 +673,7 @@ __device__ __forceinline__ void fast_dry_hour(MemberState<R> &s, const FastPar<R
     s.sgw = kOneFma ? s.sgw * p.c_gk : s.sgw - q_gw;
 }
 
-template <typename R, int kStride>
+template <typename R, int kStride, bool kNestedLadder = false>
 __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPar<R> &p, const R *kc, const double *kb,
                                                  FastCarry<R> &carry, double ex_d, int rep, R &acc, R &agw)
 {
@@ -665,16 +683,13 @@ __device__ __forceinline__ void smart_block_fast(MemberState<R> &s, const FastPa
         const BlockPar<R> b = block_par<R, kStride>(kc);
         const R hex = p.Hz * ex;                    // constant over the block
         const unsigned mask = __activemask();       // the lanes walking this wet block together
-        if (!carry.valid) {       // soil total (binary32: sum of deficits) once per block, then carried hour to hour
-            carry.tot = soil_total(s);
-            carry.valid = true;
-        }
+        if (!carry.valid) carry_form(s, carry);   // soil total (binary32: sum of deficits) once per block, then carried hour to hour
         R sum_riv = R(0);                           // river outflow of the block = r_rk * sum of the store
 #pragma unroll kWetUnroll
         for (int h = 0; h < rep; ++h) {
             R q_gw, q_in;
             sum_riv += s.riv;
-            fast_wet_hour<R, kStride>(s, p, kc, b, carry, ex, hex, mask, q_gw, q_in);
+            fast_wet_hour<R, kStride, kNestedLadder>(s, p, kc, b, carry, ex, hex, mask, q_gw, q_in);
             agw += q_gw;
         }
         acc = kOneFma ? fma(sum_riv, kc[6 * kStride], acc) : acc + sum_riv * kc[6 * kStride];

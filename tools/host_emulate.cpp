@@ -61,7 +61,7 @@ static int emulate(int mode, int rep, double area, double dt, long T, long W, co
     if (mode != 0) { s.ove += s.dra; s.sgw += s.dgw; s.dra = s.dgw = 0; }
     if (mode >= 2 && sizeof(R) == 4)      // binary32 fast form: the soil as deficits (fast_wet_soil_deficit)
         for (int k = 0; k < 6; ++k) s.ly[k] = (R)((double)p.z - v[5 + k] * to_mm);
-    FastCarry<R> carry; carry.tot = 0; carry.valid = false;
+    FastCarry<R> carry; carry.tot = carry.part = 0; carry.valid = false;
     StepOut<R> o;
     const R qscale = area / (1e3 * dt), mean_scale = area / (1e3 * dt) / (double)gap;
     long n_rep = report_type == 1 ? T / gap : (T + gap - 1) / gap;
@@ -80,7 +80,7 @@ static int emulate(int mode, int rep, double area, double dt, long T, long W, co
                 const bool wet = ex_d >= 0.0;
                 const R ex = wet ? ex_d : 0.0, hex = fp.Hz * ex;
                 if (wet) {
-                    if (!carry.valid) { carry.tot = soil_total(s); carry.valid = true; }
+                    if (!carry.valid) carry_form(s, carry);
                 } else {
                     dry_block_soil<R>(s, kc[0], fp.z, ex_d, rep);
                     carry.valid = false;

@@ -65,6 +65,18 @@ def main():
     r = eng.run(big, scores=True, gw=True, best=('KGE', 1), out={'block': blk})
     cases.append(("grouped batch with wild members", float(r["best"][0])))
     cases.append(("run_host", float(eng.run_host(big[:300])["gw"].sum())))
+    # relay: the timeline in segments, state parked in the launch workspace between two CTAs (tickets,
+    # progress counters, acquire/release hand-over); block and per-step mode, both precisions, the two
+    # step forms side by side, best member
+    from smartpy_b200 import _native
+    for flags in (_native.flag_relay_segs(3), _native.flag_relay_segs(5) | 0x10000):
+        for precision in ('f64', 'f32'):
+            eng = BatchEngine(c.rain[:n], c.peva[:n], c.area, 3600.0, 24, obs=obs, extra=EXTRA, warm_up_steps=24 * 5,
+                              gw_constraint=0.12667, precision=precision, flags=flags)
+            r = eng.run(big, scores=True, gw=True, best=('NSE', 1))
+            cases.append(("relay flags=%#x %s" % (flags, precision), float(r["best"][0])))
+            r = eng.run(params, discharge=True, scores=True, gw=True)
+            cases.append(("relay + discharge flags=%#x %s" % (flags, precision), float(r["gw"].sum())))
     # conditioning of a score table (mask + ordered compaction, radix select + bitonic sort of the
     # winners: shared-memory histograms, atomics, multi-chunk sort) and the device sampler
     from smartpy_b200.montecarlo import conditioning
