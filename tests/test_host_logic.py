@@ -285,6 +285,47 @@ def test_member_order_sizes_are_host_functions():
     assert lib.smart_launch_count() >= 0
 
 
+def test_launch_workspace_size_is_a_host_function():
+    """smart_batch_workspace_bytes needs no device.  Single-catchment launches get room for the relay
+    (2 tickets + progress counters + 26 doubles per thread of the launch, include/smart_b200.h) behind
+    the per-CTA slots of the best-member search; multi-catchment launches, launches that return the
+    state, and batches beyond the relay's range only get the best-member slots."""
+    import ctypes
+    from smartpy_b200 import _native, _build
+    _build.build()
+    lib = _native.load()
+
+    def desc(n, catchments=1, best=0, slots=0, last_state=False):
+        d = _native.BatchDesc()
+        d.n_members, d.n_steps, d.n_catchments = n, 240, catchments
+        d.members_per_catchment = n // catchments
+        d.best_sign = best
+        d.member_order_len = slots
+        d.member_order = 8 if slots else None
+        d.last_state = 8 if last_state else None
+        return d
+
+    def pad(x):
+        return (x + 127) // 128 * 128
+
+    n = 100000
+    groups = -(-n // 64)                         # 64-member CTAs for a batch of this size
+    relay = 128 + pad(4 * groups) + 8 * groups * 26 * 64
+    assert lib.smart_batch_workspace_bytes(ctypes.byref(desc(n))) == relay
+    assert lib.smart_batch_workspace_bytes(ctypes.byref(desc(n, best=1))) == pad(16 * groups) + relay
+    slots = lib.smart_member_order_len(n)        # the launch has one thread per slot of member_order
+    groups = slots // 64
+    assert lib.smart_batch_workspace_bytes(ctypes.byref(desc(n, slots=slots))) == \
+        128 + pad(4 * groups) + 8 * groups * 26 * 64
+    assert lib.smart_batch_workspace_bytes(ctypes.byref(desc(n, last_state=True))) == 0
+    assert lib.smart_batch_workspace_bytes(ctypes.byref(desc(1000000, catchments=10000))) == 0
+    blocks = 1000000 // 32                       # one-warp CTAs for whole warps per catchment
+    assert lib.smart_batch_workspace_bytes(ctypes.byref(desc(1000000, catchments=10000, best=-1))) == 16 * blocks
+    assert lib.smart_batch_workspace_bytes(ctypes.byref(desc(4000000))) == 0      # beyond the relay's range
+    assert lib.smart_batch_workspace_bytes(None) == 0
+    assert _native.flag_relay_segs(9) == 9 << 8 and _native.flag_relay_segs(300) == (300 & 0xff) << 8
+
+
 def test_binary64_unit_is_built_without_implicit_contraction():
     """The determinism of binary64 results across kernel instantiations rests on -fmad=false for
     smart_kernels.cu (tests/test_gpu_fullsize.py); the FP32-state unit keeps the default."""
