@@ -149,6 +149,7 @@ struct KArgs {
     const long long *order;      // optional grouping: thread i advances member order[i] (< 0: idle thread)
     long long n_threads;         // threads of the launch that may carry a member (N, or the length of order)
     long long N, T, W, ld_q, ld_s, ld_g;
+    long long q_stride_bytes;    // ld_q * sizeof(state type): one report row of the discharge output
     int C, mpc, gap, report_type;
     // multi-catchment thread layout (see member_of_thread): whole warps of one catchment first, the
     // remainders of all catchments packed behind them; tile geometry of the remainder region
@@ -363,8 +364,14 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
     // fall inside a block (every hour for C4a) the output cursor advances by one row per report
     // instead of being rebuilt from the report index (a 64-bit multiply-add per store); elsewhere a
     // report is rare and the index costs one register instead of a pointer.
+    // The cursor is a byte address advanced by a stride the host put in the launch arguments (an add
+    // with a constant-bank operand: no per-report reload and shift of ld_q), and whether there is an
+    // output at all is one launch-wide predicate on the store: a tail thread that shadows a member
+    // writes that member's own values to that member's own slots a second time instead of carrying a
+    // null pointer to test at every report.
     constexpr bool kCursor = kMode == kModeBlockSub;
-    R *q_out = (kCursor && a.discharge != nullptr && active) ? static_cast<R *>(a.discharge) + m : nullptr;
+    const bool has_q = kCursor && a.discharge != nullptr;
+    char *q_out = has_q ? reinterpret_cast<char *>(static_cast<R *>(a.discharge) + m) : nullptr;
     int r = 0;
 
     // Relay: this CTA walks stages [ci_begin, ci_end) of the timeline.  Everything that lives across
@@ -397,35 +404,41 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
         r = __double2loint(packed);
         carry.valid = __ldcg(pk + 25 * BLOCK) != 0.0;
         if (sizeof(R) == 8) carry.part = soil_lower(s);   // (what it held: the same five values in the same order)
-        if (q_out != nullptr) q_out += static_cast<long long>(r) * a.ld_q;
+        if (has_q) q_out += static_cast<long long>(r) * a.q_stride_bytes;
     }
-    auto report = [&](R sval) {
-        if (!kWide) {   // binary32 state: fold the per-gap sums into binary64
+    // the pieces of one report: binary32 sums folded into binary64, the value stored, the value scored
+    auto fold_sums = [&]() {
+        if (!kWide) {
             GN += static_cast<double>(agw);
             GD += static_cast<double>(aall);
             agw = aall = R(0);
         }
+    };
+    auto store = [&](R sval) {
         if (kCursor) {
-            if (q_out != nullptr) {
-                *q_out = sval;
-                q_out += a.ld_q;
-            }
+            if (has_q) *reinterpret_cast<R *>(q_out) = sval;
+            q_out += a.q_stride_bytes;
         } else if (a.discharge != nullptr && active) {
             static_cast<R *>(a.discharge)[static_cast<long long>(r) * a.ld_q + m] = sval;
         }
-        if (a.obs != nullptr) {
-            const double e = __ldg(&a.obs[static_cast<long long>(r) * a.C + c]);
-            if (e == e) {                            // montecarlo.py:195-196 NaN mask
-                const double ebar = a.obs_stats[c * SMART_OBS_STATS + 2];
-                const double ds = static_cast<double>(sval) - ebar;
-                const double de = e - ebar;
-                const double df = ds - de;
-                A += ds;
-                B = fma(ds, ds, B);
-                Cc = fma(ds, de, Cc);
-                E = fma(df, df, E);
-            }
+    };
+    auto score = [&](R sval) {
+        const double e = __ldg(&a.obs[static_cast<long long>(r) * a.C + c]);
+        if (e == e) {                            // montecarlo.py:195-196 NaN mask
+            const double ebar = a.obs_stats[c * SMART_OBS_STATS + 2];
+            const double ds = static_cast<double>(sval) - ebar;
+            const double de = e - ebar;
+            const double df = ds - de;
+            A += ds;
+            B = fma(ds, ds, B);
+            Cc = fma(ds, de, Cc);
+            E = fma(df, df, E);
         }
+    };
+    auto report = [&](R sval) {
+        fold_sums();
+        store(sval);
+        if (a.obs != nullptr) score(sval);
         ++r;
     };
 
@@ -514,18 +527,27 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
             };
             // gap == 1: every step is a report ('raw' and 'summary' coincide) -- no countdown, no
             // per-gap sum; the fast form keeps the sum of Q_out for the groundwater share
-            auto every_hour = [&](R q_riv, R q_gw, R q_all) {
-                agw += q_gw;
-                if (kFast) {
-                    if (kWide) aall += q_riv;
-                    else acc += q_riv;
-                } else {
-                    aall += q_all;
-                }
-                if (in_main) report(q_riv * scale);
-            };
-            auto rows = [&](auto hourly_tag) {
+            // (the warm-up / main-run and scored / unscored cases are separate copies of the hour loop:
+            // as run-time tests they cost ~10 instructions in every hour of C4a)
+            auto rows = [&](auto hourly_tag, auto main_tag, auto scored_tag) {
                 constexpr bool kHourly = decltype(hourly_tag)::value;
+                constexpr bool kMain = decltype(main_tag)::value, kScored = decltype(scored_tag)::value;
+                auto every_hour = [&](R q_riv, R q_gw, R q_all) {
+                    agw += q_gw;
+                    if (kFast) {
+                        if (kWide) aall += q_riv;
+                        else acc += q_riv;
+                    } else {
+                        aall += q_all;
+                    }
+                    if constexpr (kMain) {
+                        const R sval = q_riv * scale;
+                        fold_sums();
+                        store(sval);
+                        if constexpr (kScored) score(sval);
+                        ++r;
+                    }
+                };
                 auto done = [&](R q_riv, R q_gw, R q_all) {
                     if constexpr (kHourly) every_hour(q_riv, q_gw, q_all);
                     else after_hour(q_riv, q_gw, q_all);
@@ -570,13 +592,15 @@ __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, 
                 }
             };
             if (a.gap == 1) {
-                rows(std::true_type{});
+                if (!in_main) rows(std::true_type{}, std::false_type{}, std::false_type{});
+                else if (a.obs != nullptr) rows(std::true_type{}, std::true_type{}, std::true_type{});
+                else rows(std::true_type{}, std::true_type{}, std::false_type{});
                 if (!kWide && kFast && in_main) {   // binary32 state: the chunk's sum of Q_out joins the binary64 sum
                     GD += static_cast<double>(acc);
                     acc = R(0);
                 }
             } else {
-                rows(std::false_type{});
+                rows(std::false_type{}, std::false_type{}, std::false_type{});   // (tags unused: run-time tests in after_hour)
             }
         } else {
             // wet/dry driver of the fast step, formed one step ahead of the state
@@ -1289,6 +1313,7 @@ int launch(const smart_batch_desc *d, cudaStream_t stream)
     a.T = d->n_steps;
     a.W = d->initial_state ? 0 : d->n_warmup;
     a.ld_q = d->ld_discharge;
+    a.q_stride_bytes = d->ld_discharge * static_cast<long long>(sizeof(R));
     a.C = d->n_catchments;
     a.mpc = d->n_catchments > 1 ? d->members_per_catchment : 1;
 

@@ -150,6 +150,35 @@ def test_block_sub_mode_matches_oracle(catchment, oracle_lib, gap, report, preci
         assert abs(float(res["gw"][m]) - gw_ref) < (1e-9 if precision == "f64" else 1e-4) * gw_ref
 
 
+@pytest.mark.parametrize("gap,report", [(1, "raw"), (6, "summary")])
+def test_block_sub_mode_scores_fused_with_the_hourly_reports(catchment, gap, report):
+    """Reports inside the day WITH observations: the scores the kernel accumulates report by report
+    equal the objective functions of the series it wrote (oracle/scores.py on the returned discharge),
+    NaN observations skipped; 40 members in a 64-thread CTA, so tail threads shadow the last member."""
+    from oracle import scores as oscores
+    from smartpy_b200.engine import BatchEngine, warm_up_length
+    g = load_golden("runs_members")
+    days = 300
+    n = days * 24
+    rng = np.random.RandomState(5)
+    obs = np.abs(rng.randn(n // gap)) * 3.0 + 0.5
+    obs[rng.rand(n // gap) < 0.15] = np.nan
+    eng = BatchEngine(catchment.rain[:n:24] * 24.0, catchment.peva[:n:24] * 24.0, catchment.area, 3600.0, gap,
+                      obs=obs, extra=EXTRA, warm_up_steps=warm_up_length(30, 3600.0), report=report,
+                      gw_constraint=0.12667, forcing_repeat=24)
+    assert eng._block_mode(None, False)
+    res = eng.run(g["params"], discharge=True, scores=True, gw=True)
+    q = res["discharge"].cpu().numpy().T
+    sc = res["scores"].cpu().numpy()
+    gw = res["gw"].cpu().numpy()
+    ref = oscores.score_members(q, gw, obs, 0.12667)
+    assert np.max(np.abs(sc[:, :7] - ref[:, :7]) / np.maximum(1.0, np.abs(ref[:, :7]))) < 1e-10
+    assert np.array_equal(sc[:, 7], ref[:, 7])
+    # scores-only run of the same engine: same bits without the output
+    sc_only = eng.run(g["params"], discharge=False, scores=True, gw=True)["scores"].cpu().numpy()
+    assert np.array_equal(sc_only, sc)
+
+
 def test_block_constant_hourly_series_is_detected_for_hourly_reports(catchment):
     """A per-step series that is constant inside days (what timeframe.py:167-186 produces) with
     HOURLY reporting: the engine folds it to one row per day (smart_fold_blocks) and the run takes
