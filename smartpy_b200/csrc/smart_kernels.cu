@@ -233,13 +233,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 __host__ __device__ __forceinline__ int stage_doubles(int chunk, int kc) { return ((chunk + 1) * kc + 15) & ~15; }
 
 // ------------------------------------------------------------------ shared-memory layout of one CTA
-//   [0, 128)                       two mbarriers (TMA stages), padded
-//   double rain[2][chunk * kc]     forcing stages
-//   double peva[2][chunk * kc]
+//   [0, 128)                       two mbarriers (TMA stages), relay ticket, padded
 //   double acc[kAccSlots][BLOCK]   per-thread binary64 accumulators touched once per report step
 //   R      kconst[kConstSlots][BLOCK]  per-thread constants of the fast step (see smart_step_fast)
 //   double td[BLOCK]               parameter T in binary64 (wet/dry predicate)
 //   double kblock[kBlockSlots][BLOCK]  dry-block constants (block mode only, see smart_block_fast)
+//   double rain[2][chunk * kc]     forcing stages
+//   double peva[2][chunk * kc]
 enum : int { kVariantFast = 0, kVariantGeneral = 1, kVariantFluxes = 2 };
 // How the time loop reads the forcing (host: mode_of):
 //   kModeStep     one forcing row per step;
@@ -250,7 +250,10 @@ enum : int { kVariantFast = 0, kVariantGeneral = 1, kVariantFluxes = 2 };
 //                 and the stores walked hour by hour (every hour's outflow is reported or summed).
 enum : int { kModeStep = 0, kModeBlock = 1, kModeBlockSub = 2 };
 
-template <typename R, int BLOCK>
+// The per-thread columns come FIRST, at offsets known at compile time (the stages, whose size
+// depends on the launch, follow them): an access is then `[tid * 8 + constant]` instead of an
+// address rebuilt from the stage size at every use.
+template <typename R, int BLOCK, int kMode>
 struct Smem {
     uint64_t *full;
     double *rain, *peva, *acc;
@@ -259,12 +262,12 @@ struct Smem {
     __device__ __forceinline__ Smem(unsigned char *raw, int tile)   // tile = stage_doubles(chunk, kc)
     {
         full = reinterpret_cast<uint64_t *>(raw);
-        rain = reinterpret_cast<double *>(raw + kSmemHeader);
-        peva = rain + 2 * tile;
-        acc = peva + 2 * tile;
+        acc = reinterpret_cast<double *>(raw + kSmemHeader);
         kconst = reinterpret_cast<R *>(acc + kAccSlots * BLOCK);
         td = reinterpret_cast<double *>(kconst + (kConstSlots + 1) * BLOCK);   // +1: keeps 8-byte alignment for R = float
         kblock = td + BLOCK;
+        rain = kblock + (kMode == kModeBlock ? kBlockSlots : 0) * BLOCK;       // (128-byte aligned: BLOCK >= 32)
+        peva = rain + 2 * tile;
     }
 };
 
@@ -275,7 +278,7 @@ struct Smem {
 // whole block at a time (smart_block_fast).  kModeBlockSub: reports fall inside the block.
 template <typename R, int kVariant, int BLOCK, bool kSingle, int kMode>
 __device__ __forceinline__ bool run_timeline(const KArgs &a, MemberState<R> &s, const MemberPar<R> &p,
-                                             const FastPar<R> &fp_, const Smem<R, BLOCK> &sm, long long m, bool active,
+                                             const FastPar<R> &fp_, const Smem<R, BLOCK, kMode> &sm, long long m, bool active,
                                              int c, int col, int c_base, int kc_cta, int chunk, double area,
                                              double &gw_out, StepOut<R> &o, int seg, double *park)
 {
@@ -768,7 +771,7 @@ __device__ __forceinline__ void run_member(const KArgs &a, unsigned char *smem_r
 {
     constexpr bool kFast = kVariant == kVariantFast;
     const int tid = threadIdx.x;
-    const Smem<R, BLOCK> sm(smem_raw, stage_doubles(chunk, kSingle ? 1 : kc_cta));
+    const Smem<R, BLOCK, kMode> sm(smem_raw, stage_doubles(chunk, kSingle ? 1 : kc_cta));
     const double T = par[0], C = par[1], H = par[2], D = par[3], S = par[4], Z = par[5];
     const double SK = par[6], FK = par[7], GK = par[8], RK = par[9];
     MemberPar<R> p;
