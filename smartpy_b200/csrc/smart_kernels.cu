@@ -1000,10 +1000,11 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
     if (seg > 0) {   // relay: the previous segment of this group must be done (its state parked)
         if (tid == 0) {
             int done;
-            for (;;) {
+            for (unsigned spins = 0;; ++spins) {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.relay_progress + blk) : "memory");
                 if (done >= seg) break;
                 __nanosleep(256);
+                if (spins > (1u << 28)) __trap();   // (a minute: a lost hand-over becomes an error, not a hung GPU)
             }
         }
         __syncthreads();

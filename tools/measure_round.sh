@@ -41,6 +41,9 @@ for v in "perstep --flags 65536" "general --flags 1" "1m --members 1000000" "c5_
   set -- $v; n=$1; shift
   python bench.py --steps 3 --no-cpu-baseline --no-also "$@" > $O/bench_${R}_c2_$n.json
 done
+compute-sanitizer --tool memcheck python tools/sanitizer_cases.py 2>&1 | tail -40 > $O/${R}_sanitizer_memcheck.txt
+compute-sanitizer --tool racecheck python tools/sanitizer_cases.py 2>&1 | tail -40 > $O/${R}_sanitizer_racecheck.txt
+python tools/wild_members_bench.py > $O/${R}_wild_members.json 2>&1
 python tests/parity_report.py > $O/${R}_parity_report.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/${R}_smi.csv
 ls -la $O | tail -40
