@@ -387,10 +387,7 @@ def measure(ctx, name, precision, steps, warmup, members=None, flags=0, do_e2e=T
     def host_step_with_discharge():
         # run_host with the [t][member] discharge kept on the device (70 GB at C4a: it stays sharded
         # where it was written); parameters in and the [n, 9] block out as run_host does
-        p_pin = eng._pinned('params', w["params"].shape, torch.float64)
-        p_pin.copy_(torch.from_numpy(w["params"]))
-        p_stage = eng._device_buffer('params', w["params"].shape)
-        p_stage.copy_(p_pin, non_blocking=True)
+        p_stage = eng.stage_params(w["params"])
         eng.run(p_stage, discharge=True, scores=scored, gw=True, out=out)
         blk_pin = eng._pinned('block', out["block"].shape, torch.float64)
         blk_pin.copy_(out["block"], non_blocking=True)
