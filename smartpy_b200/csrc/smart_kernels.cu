@@ -999,12 +999,18 @@ __global__ void __maxnreg__(MAX_REGS) smart_batch_kernel(const KArgs a)
 
     if (seg > 0) {   // relay: the previous segment of this group must be done (its state parked)
         if (tid == 0) {
+            // Polling costs issue slots the working warps of the SM want (with fewer groups than
+            // slots every unit waits for its predecessor: at a fixed 256 ns the polls were 10 % of all
+            // instructions the FP32 kernel executed on C5, 4 % on C2), so the pause doubles up to 8 us --
+            // a unit lasts ~0.5 ms.
             int done;
+            unsigned pause = 256;
             for (unsigned spins = 0;; ++spins) {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.relay_progress + blk) : "memory");
                 if (done >= seg) break;
-                __nanosleep(256);
-                if (spins > (1u << 28)) __trap();   // (a minute: a lost hand-over becomes an error, not a hung GPU)
+                __nanosleep(pause);
+                if (pause < 8192) pause <<= 1;
+                if (spins > (1u << 23)) __trap();   // (a minute: a lost hand-over becomes an error, not a hung GPU)
             }
         }
         __syncthreads();

@@ -331,11 +331,18 @@ __device__ __forceinline__ void fast_wet_soil_deficit(MemberState<float> &s, con
         return fits;
     };
     // most often the first layer takes everything; a lane's own branch (round 1 voted over the warp:
-    // four more instructions per hour, and the lanes that are done would run the ladder as no-ops)
-    if (!fill(0)) {
+    // four more instructions per hour, and the lanes that are done would run the ladder as no-ops),
+    // the top layer written out so that the usual path issues no selects
+    const float t0 = s.ly[0] + u;
+    if (sign_clear(t0)) {
+        s.ly[0] = t0;
+        u = 0.0f;
+    } else {
+        s.ly[0] = 0.0f;
+        u = t0;
         fill(1); fill(2); fill(3); fill(4); fill(5);
+        in_quick = fma(D, -u, in_quick);            // + D * saturation excess (:376)
     }
-    in_quick = fma(D, -u, in_quick);                // + D * saturation excess (:376)
     const float sp = p.Sz * tot;                    // :379
     float pw[6];
     pw[0] = sp;
@@ -398,8 +405,20 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
         u = fits ? zero : t;
         return fits;
     };
-    // most often the first layer takes everything; a lane's own branches (no vote, no mask to carry)
-    if (!fill(0)) {
+    // most often the first layer takes everything; a lane's own branches (no vote, no mask to carry).
+    // Saturation excess (-u after the ladder, :376-377) only exists on that path, so its two
+    // products are formed there and the usual hour does not issue them.
+    R sat_int = zero;
+    // (the top layer written out as a branch: on the usual path the level is w and nothing flows on,
+    // with no selects to issue)
+    const R w0 = s.ly[0] - u;
+    const R t0 = p.z - w0;
+    if (sign_clear(t0)) {
+        s.ly[0] = w0;
+        u = zero;
+    } else {
+        s.ly[0] = p.z;
+        u = t0;
         if (kNestedLadder) {
             // one branch per layer: the water stops at the first layer with room
             if (!fill(1)) {
@@ -413,9 +432,9 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
             fill(1); fill(2); fill(3); fill(4); fill(5);
         }
         lower = soil_lower(s);                      // the rain went below the top layer: re-sum the lower five
+        in_quick = fma(D, -u, in_quick);            // + D * saturation excess (:376)
+        sat_int = omD * (-u);                       // (1 - D) * saturation excess (:377)
     }
-    in_quick = fma(D, -u, in_quick);                // + D * saturation excess (:376)
-    in_int = omD * (-u);                            // (1 - D) * saturation excess (:377)
     const R sp = p.Sz * tot;                        // :379
     R pw[6];
     pw[0] = sp;
@@ -431,7 +450,7 @@ __device__ __forceinline__ void fast_wet_soil(MemberState<R> &s, const FastPar<R
 #pragma unroll
         for (int i = 0; i < 6; ++i) s.ly[i] = fma(-s.ly[i], pw[i], s.ly[i]);            // :381-385
         const R tot1 = soil_total(s);
-        in_int = fma(omD, -u, tot_f - tot1);                                            // :377 + interflow
+        in_int = sat_int + (tot_f - tot1);                                              // :377 + interflow
 #pragma unroll
         for (int i = 0; i < 6; ++i) {                                                   // :388-399
             const R f2 = i == 0 ? sp : sp * inv_const<R>(i);
