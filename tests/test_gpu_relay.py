@@ -105,13 +105,15 @@ def test_relay_with_grouped_members_wild_members_and_best_member(catchment):
     assert plain["best"][1] == int(np.nanargmax(plain["scores"][:, 0]))
 
 
-def test_relay_is_what_a_c2_sized_batch_runs_and_changes_no_bit(catchment):
-    """C2's size: the library chooses the relay on its own (no flag); same bits as the plain launch."""
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_relay_is_what_a_c2_sized_batch_runs_and_changes_no_bit(catchment, precision):
+    """C2's size (C5 with binary32 state): the library chooses the relay on its own (no flag); same
+    bits as the plain launch."""
     import bench
     n = 100000
     params = bench.lhs_rows(n, 42)
-    auto = _run(catchment, params, 0, discharge=False)                           # plain launch
-    eng = make_engine(catchment)                                                 # library's choice
+    auto = _run(catchment, params, 0, discharge=False, precision=precision)      # plain launch
+    eng = make_engine(catchment, precision=precision)                            # library's choice
     res = eng.run(params, discharge=False, scores=True, gw=True)
     assert np.array_equal(res["scores"].cpu().numpy(), auto["scores"], equal_nan=True)
     assert np.array_equal(res["gw"].cpu().numpy(), auto["gw"])
