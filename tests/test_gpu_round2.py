@@ -319,6 +319,22 @@ def test_scores_and_gw_written_into_a_gather_block(catchment):
         eng.run(g["params"], scores=True, out={"block": blk[:, :8]})
 
 
+def test_run_host_takes_page_locked_rows_without_a_staging_copy(catchment):
+    """run_host() with the engine's pinned_rows() buffer: same bits as with a numpy array."""
+    import torch
+    g = load_golden("runs_members")
+    eng = make_engine(catchment)
+    ref = eng.run_host(g["params"], copy=True)
+    rows = eng.pinned_rows(len(g["params"]))
+    assert rows.is_pinned() and rows.shape == (40, 10) and rows.dtype == torch.float64
+    rows.numpy()[:] = g["params"]
+    out = eng.run_host(rows, copy=True)
+    assert np.array_equal(out["scores"], ref["scores"], equal_nan=True) and np.array_equal(out["gw"], ref["gw"])
+    # a tensor that is not page-locked falls back to the staged path
+    out2 = eng.run_host(torch.from_numpy(g["params"].copy()), copy=True)
+    assert np.array_equal(out2["scores"], ref["scores"], equal_nan=True)
+
+
 def test_run_host_round_trip_reuses_its_staging(catchment):
     g = load_golden("runs_members")
     eng = make_engine(catchment, n_steps=24 * 300, warm_up_days=30)
