@@ -182,6 +182,13 @@ def csrc_hash():
     return h.hexdigest()[:16]
 
 
+def capture_for(captures, key, sha):
+    """The ncu capture (profiles/ncu_traffic.json) of workload `key`, and whether it counts: only a
+    capture of the very sources that are running (csrc_sha) may feed roofline.frac_pipe / traffic."""
+    cap = captures.get(key) or {}
+    return cap, bool(cap) and cap.get("csrc_sha") == sha
+
+
 # ---------------------------------------------------------------------------------------- clocks
 class ClockSampler(object):
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -437,8 +444,7 @@ def measure(ctx, name, precision, steps, warmup, members=None, flags=0, do_e2e=T
     hbm_bytes_per_step = n * (80 + 64 + 8) + 2 * 8 * w["rain"].size + q_bytes
     hbm_peak = ctx.peaks.get("hbm_gbs", 6650.0)
     key = "{}:{}:{}:{}".format(name, n, precision, flags)
-    cap = ctx.captures.get(key) or {}
-    cap_ok = bool(cap) and cap.get("csrc_sha") == ctx.hash
+    cap, cap_ok = capture_for(ctx.captures, key, ctx.hash)
     inst = cap.get("fp64_inst_per_step" if bits == 64 else "fp32_inst_per_step") if cap_ok else None
     frac_alg = per_gpu * i_alg / peak_fma
     frac_pipe = per_gpu * inst / peak_fma if inst else None

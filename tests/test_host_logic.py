@@ -453,3 +453,19 @@ def test_no_netcdf_code_is_left_unexecuted():
         inout.read_rain_file('nowhere.nc', 'netcdf')
     with pytest.raises(Exception, match="netCDF4"):
         inout.write_flow_file_from_nds([], [], 'nowhere', 'netcdf')
+
+
+def test_bench_only_uses_captures_of_the_running_sources():
+    """bench.py folds ncu evidence into its line only when the capture was taken from the sources
+    that run (round 1 injected an instruction count of older sources)."""
+    import bench
+    sha = bench.csrc_hash()
+    assert len(sha) == 16 and sha == bench.csrc_hash()
+    table = {"c2:100000:f64:0": {"csrc_sha": sha, "fp64_inst_per_step": 28.0},
+             "c3:1250000:f64:0": {"csrc_sha": "0" * 16, "fp64_inst_per_step": 30.0}}
+    cap, ok = bench.capture_for(table, "c2:100000:f64:0", sha)
+    assert ok and cap["fp64_inst_per_step"] == 28.0
+    cap, ok = bench.capture_for(table, "c3:1250000:f64:0", sha)
+    assert not ok and cap["csrc_sha"] == "0" * 16          # stale: reported as such, not used
+    cap, ok = bench.capture_for(table, "c5:100000:f32:0", sha)
+    assert not ok and cap == {}
