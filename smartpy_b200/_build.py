@@ -14,9 +14,11 @@ UNITS = [
     ("smart_kernels_f32.cu", []),
     ("smart_select.cu", []),
     ("smart_sample.cu", []),
+    ("smart_io.cpp", []),          # host-side bulk text I/O of the sample database (include/smart_b200_io.h)
 ]
 SOURCES = [os.path.join(_CSRC, name) for name, _ in UNITS]
-HEADERS = [os.path.join(_CSRC, "smart_step.cuh"), os.path.join(ROOT, "include", "smart_b200.h")]
+HEADERS = [os.path.join(_CSRC, "smart_step.cuh"), os.path.join(ROOT, "include", "smart_b200.h"),
+           os.path.join(ROOT, "include", "smart_b200_io.h")]
 LIB_PATH = os.path.join(_HERE, "libsmart_b200.so")
 OBJ_DIR = os.path.join(_CSRC, "_obj")
 
@@ -59,7 +61,7 @@ def build(force=False, verbose=False):
         log.append(out)
         if proc.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + out)
-    log.append(_run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objects))
+    log.append(_run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + objects + ["-lpthread"]))
     text = "".join(log)
     if verbose:
         print(text)

@@ -43,6 +43,8 @@ SYMBOLS = (
     "smart_condition_workspace_bytes", "smart_condition_rows", "smart_best_rows",
     "smart_lhs_rows",
 )
+# ... and include/smart_b200_io.h (host-side bulk text I/O of the sample database)
+IO_SYMBOLS = ("smart_csv_bound", "smart_csv_format_f32", "smart_csv_parse_f32")
 
 MAX_CONDITIONS = 8
 COND_KINDS = {'equal': 0, 'min': 1, 'max': 2, 'inside': 3, 'outside': 4}
@@ -180,6 +182,14 @@ def load():
     lib.smart_lhs_rows.restype = ctypes.c_int
     lib.smart_lhs_rows.argtypes = [ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.smart_csv_bound.restype = ctypes.c_int64
+    lib.smart_csv_bound.argtypes = [ctypes.c_int64, ctypes.c_int32]
+    lib.smart_csv_format_f32.restype = ctypes.c_int64
+    lib.smart_csv_format_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                         ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32]
+    lib.smart_csv_parse_f32.restype = ctypes.c_int64
+    lib.smart_csv_parse_f32.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p,
+                                        ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32]
     _lib = lib
     return lib
 

@@ -469,3 +469,52 @@ def test_bench_only_uses_captures_of_the_running_sources():
     assert not ok and cap["csrc_sha"] == "0" * 16          # stale: reported as such, not used
     cap, ok = bench.capture_for(table, "c5:100000:f32:0", sha)
     assert not ok and cap == {}
+
+
+def test_sample_database_text_is_numpys_byte_for_byte():
+    """include/smart_b200_io.h: the library formats and parses the rows of the sample database
+    (montecarlo.py:211-231 writer, :233-262 reader) on all host cores.  The bytes must be those of
+    numpy.savetxt(fmt='%.6e') -- Python's correctly rounded '%.6e' of the float32 value -- and the
+    values read back those of text -> binary64 -> float32, on ordinary values, the whole exponent
+    range, exact ties of the seventh digit, neighbours of the powers of ten, random bit patterns and
+    the non-finite values (the GW column is NaN when the constraint is off)."""
+    import io
+    from smartpy_b200 import _native, _build
+    from smartpy_b200.montecarlo import database as db
+    _build.build()
+    lib = _native.load()
+    assert all(hasattr(lib, name) for name in _native.IO_SYMBOLS)
+    rng = np.random.RandomState(3)
+
+    def check(table):
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        text = db.format_rows(table)
+        ref = io.BytesIO()
+        np.savetxt(ref, table, fmt='%.6e', delimiter=',')
+        assert text == ref.getvalue()
+        cols = list(range(table.shape[1]))[::-1] + [0]
+        back = db.parse_rows(text, table.shape[1], cols)
+        want = np.loadtxt(io.BytesIO(text), delimiter=',', dtype=np.float64, ndmin=2).astype(np.float32)[:, cols]
+        assert np.array_equal(back, want, equal_nan=True)
+
+    check(np.abs(rng.randn(5000, 18)) * 50)
+    check(rng.randn(5000, 7) * 10.0 ** rng.randint(-44, 38, (5000, 7)))
+    k = rng.randint(1000000, 8388607, (5000, 3))
+    check(k + 0.5)                       # seventh digit exactly half way: ties to even
+    check((k + 0.5) / 1024.0)
+    check((k + 0.5) * 4096.0)
+    check(rng.randint(0, 2 ** 32, (20000, 5)).astype(np.uint32).view(np.float32))
+    powers = np.array([[10.0 ** e for e in range(-45, 39)]], dtype=np.float32)
+    check(powers)
+    check(np.nextafter(powers, np.float32(0)))
+    check(np.nextafter(powers, np.float32(np.inf)))
+    check(np.array([[0.0, -0.0, np.nan, np.inf, -np.inf, 1e-45, 3.4028235e38, 9.9999995e6, 99999996.0, 0.1]]))
+    # text this library did not write (more digits, no exponent, spaces) goes through strtod
+    loose = b"1.5,-2.25e3, 7\n0.1234567891234,1e-400,1e400\n"
+    got = db.parse_rows(loose, 3, [0, 1, 2])
+    assert np.array_equal(got, np.array([[1.5, -2250.0, 7.0], [0.1234567891234, 0.0, np.inf]], dtype=np.float32))
+    with pytest.raises(ValueError):
+        db.parse_rows(b"1.0,2.0\n3.0\n", 2, [0, 1])
+    # a block boundary inside write_rows / an empty table
+    assert db.format_rows(np.zeros((0, 4), dtype=np.float32)) == b""
+    assert lib.smart_csv_format_f32(None, 1, 1, 1, None, 0, 0) == _native.ERR_BAD_ARG

@@ -15,7 +15,7 @@ obj_dir = os.path.join(out_dir, "obj_" + name)
 os.makedirs(obj_dir, exist_ok=True)
 procs, objects = [], []
 for unit, flags in _build.UNITS:
-    obj = os.path.join(obj_dir, unit.replace(".cu", ".o"))
+    obj = os.path.join(obj_dir, os.path.splitext(unit)[0] + ".o")
     objects.append(obj)
     cmd = ["nvcc"] + _build.NVCC_FLAGS + flags + extra + ["-I", os.path.join(ROOT, "include"), "-c",
                                                          os.path.join(ROOT, "smartpy_b200", "csrc", unit), "-o", obj]
