@@ -259,7 +259,10 @@ def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "smart_b200.h")).read()
     declared = set(re.findall(r"^(?:int|int64_t|size_t|const char \*)\s*\*?\s*(smart_\w+)\(", header, flags=re.M))
     assert declared == set(_native.SYMBOLS)
-    for name in declared:
+    io_header = open(os.path.join(ROOT, "include", "smart_b200_io.h")).read()
+    declared_io = set(re.findall(r"^(?:int|int64_t|size_t|const char \*)\s*\*?\s*(smart_\w+)\(", io_header, flags=re.M))
+    assert declared_io == set(_native.IO_SYMBOLS)
+    for name in declared | declared_io:
         assert hasattr(lib, name), name
     assert lib.smart_version() == 200
     # argument validation happens before any CUDA call, so it is testable without a GPU
