@@ -64,9 +64,8 @@ class SampleDatabase(object):
                 raise ValueError("the database keeps the simulated series: simulations [n, {}] required".format(
                     self.n_series))
             blocks.append(np.asarray(simulations))
-        table = np.ascontiguousarray(np.concatenate(blocks, axis=1), dtype=np.float32)   # '%.6e' of the float32 value, montecarlo.py:226-231
-        self._handle.write(format_rows(table))
-        self.rows_written += table.shape[0]
+        write_formatted(self._handle, blocks)      # '%.6e' of the float32 value, montecarlo.py:226-231
+        self.rows_written += blocks[0].shape[0]
 
     def close(self, compression=None):
         if self._handle is not None:
@@ -78,20 +77,41 @@ class SampleDatabase(object):
             os.remove(self.path)
 
 
-def format_rows(table):
-    """float32 [n, k] -> the bytes numpy.savetxt(fmt='%.6e', delimiter=',') would write."""
+def write_formatted(handle, column_blocks):
+    """Write the rows [block_0 | block_1 | ...] (arrays with the same number of rows, any float type)
+    to the binary handle as numpy.savetxt(fmt='%.6e', delimiter=',') of their float32 rounding would.
+    Blocks of _BLOCK_ROWS rows at a time: the float32 row buffer and the text buffer are allocated
+    once and reused, and the text goes to the handle without a copy."""
     lib = _native.load()
-    table = np.ascontiguousarray(table, dtype=np.float32)
-    n, k = table.shape
-    pieces = []
-    for first in range(0, n, _BLOCK_ROWS):
-        rows = table[first:first + _BLOCK_ROWS]
-        out = np.empty(int(lib.smart_csv_bound(rows.shape[0], k)), dtype=np.uint8)
-        written = lib.smart_csv_format_f32(rows.ctypes.data, rows.shape[0], k, k, out.ctypes.data, out.size, 0)
+    column_blocks = [np.asarray(b) for b in column_blocks]
+    n = column_blocks[0].shape[0]
+    k = sum(b.shape[1] for b in column_blocks)
+    if any(b.ndim != 2 or b.shape[0] != n for b in column_blocks):
+        raise ValueError("column blocks must be 2-D with the same number of rows")
+    if n == 0:
+        return
+    step = min(n, _BLOCK_ROWS)
+    rows = np.empty((step, k), dtype=np.float32)
+    text = np.empty(int(lib.smart_csv_bound(step, k)), dtype=np.uint8)
+    view = memoryview(text)
+    for first in range(0, n, step):
+        m = min(step, n - first)
+        col = 0
+        for b in column_blocks:                      # (the cast to float32 happens in this copy)
+            rows[:m, col:col + b.shape[1]] = b[first:first + m]
+            col += b.shape[1]
+        written = lib.smart_csv_format_f32(rows.ctypes.data, m, k, k, text.ctypes.data, text.size, 0)
         if written < 0:
             _native.check(int(written))
-        pieces.append(out[:written].tobytes())
-    return b''.join(pieces)
+        handle.write(view[:written])
+
+
+def format_rows(table):
+    """float [n, k] -> the bytes numpy.savetxt(fmt='%.6e', delimiter=',') would write for its float32
+    rounding."""
+    sink = io.BytesIO()
+    write_formatted(sink, [np.asarray(table)])
+    return sink.getvalue()
 
 
 def parse_rows(text, n_columns, wanted):
